@@ -1,0 +1,152 @@
+// common.cuh -- host/device plumbing shared by every op of the trajectory-return path.
+//
+// sm_100a only.  No torch types: this translation unit family builds into the C-ABI library
+// declared in include/hpc_rll_b200.h.
+//
+// Replaces (re-derived, not copied) the reference's helper headers
+//   include/hpc/rll/cuda/status.h:15-28  (checkCudaErr -> std::logic_error)  -> error codes + message
+//   include/hpc/rll/cuda/reduce.h:13-99  (warp/block reductions)             -> reduce.cuh
+//   include/hpc/rll/cuda/common.h:44-45  (DEFAULT_WARP_NUM / WARP_SIZE)      -> per-kernel constants
+#pragma once
+
+#include <cuda.h>  // CUtensorMap + enums only; the driver entry point is fetched at run time
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/hpc_rll_b200.h"
+
+namespace hpcrll {
+
+// ----------------------------------------------------------------------------------------------
+// error reporting (thread-local message, C-ABI returns the code)
+// ----------------------------------------------------------------------------------------------
+int set_error(int code, const char* fmt, ...);
+void clear_error();
+
+#define HPC_REQUIRE(cond, ...)                                          \
+    do {                                                                \
+        if (!(cond)) return ::hpcrll::set_error(HPC_RLL_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+#define HPC_CUDA(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return ::hpcrll::set_error(HPC_RLL_ECUDA, "%s failed: %s (%s:%d)", #expr,             \
+                                       cudaGetErrorString(e__), __FILE__, __LINE__);              \
+    } while (0)
+
+#define HPC_LAUNCH_CHECK() HPC_CUDA(cudaGetLastError())
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// number of SMs of the current device (cached)
+int sm_count();
+
+// every kernel launch of the library is counted (hpc_rll_launch_count)
+void count_launch(int n = 1);
+
+// ----------------------------------------------------------------------------------------------
+// TMA descriptors (host).  2-D fp32 row-major view: rows x cols, row pitch ld (elements).
+// Requirements: base 16B aligned, ld*4 % 16 == 0.  OOB elements of a box read as zero.
+// ----------------------------------------------------------------------------------------------
+bool tma_ok_2d(const void* base, int64_t cols, int64_t ld);
+int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                 int box_cols);
+
+// Opt a kernel into > 48 KB dynamic shared memory, once per device (the attribute is per context).
+struct SmemOptIn {
+    bool done[64] = {};
+    template <typename K>
+    int ensure(K kernel, int bytes) {
+        int dev = 0;
+        HPC_CUDA(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && done[dev]) return HPC_RLL_OK;
+        HPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        HPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+        if (dev >= 0 && dev < 64) done[dev] = true;
+        return HPC_RLL_OK;
+    }
+};
+
+// scratch requirement of each op (defined next to the op's kernels; runtime.cu dispatches)
+size_t workspace_bytes(int op, int64_t T, int64_t B, int64_t N);
+
+// debug/tuning knob: HPC_RLL_CFG_<op> environment override or hpc_rll_debug_set_config()
+int tuning_config(int op);
+
+// ----------------------------------------------------------------------------------------------
+// device: mbarrier + TMA PTX wrappers
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make mbarrier.init visible to the async proxy (TMA) before the first copy targets it
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// 2-D tiled TMA load: box at (col0,row0) of the tensor map -> smem, completes on `bar`
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int col0, int row0, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(col0), "r"(row0), "r"(smem_u32(bar))
+        : "memory");
+}
+// 1-D bulk copy global -> smem (bytes % 16 == 0, both 16B aligned), completes on `bar`
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// streaming (evict-first) global accesses for data touched exactly once
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream4(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream4(const float4* p) { return __ldcs(p); }
+
+#endif  // __CUDACC__
+
+}  // namespace hpcrll

@@ -1,0 +1,493 @@
+// gae.cu -- Generalized Advantage Estimation, forward and adjoint, for sm_100a.
+//
+// Semantics: hpc_rll/origin/gae.py:28-37 (normalised GAE):
+//     delta_t = r_t + gamma*v_{t+1} - v_t
+//     d_t     = 1 + lambda*d_{t+1}            (d_T = 0; a Python double in origin)
+//     g_t     = d_t*delta_t + gamma*lambda*g_{t+1}
+//     adv_t   = g_t / d_t
+// Replaces the reference's GaeForward (src/rl_utils/gae.cu:8-28) and gaeForwardKernel
+// (include/hpc/rll/cuda/rl_utils/gae_kernel.h:10-29: one thread per column, <<<B/32,32>>>,
+// three dependent scalar loads per step).  The reference has NO backward
+// (hpc_rll/rl_utils/gae.py:16-18 returns None); gae_bwd here is the exact adjoint
+// (SURVEY.md A.1), a forward-in-time scan:
+//     ghat_t = G_t/d_t + gamma*lambda*ghat_{t-1};  dd_t = d_t*ghat_t
+//     grad_reward_t = dd_t;   grad_value_t = gamma*dd_{t-1} - dd_t  (dd_{-1}=0, dd_T=0)
+//
+// B200 design: ScanPipe (scan_pipe.cuh) -- (TT x BT) boxes of value/reward (fwd) or grad_adv (bwd)
+// plus the d_t slice are TMA-staged through a shared-memory ring; BT consumer threads own one
+// column each, carry (g, v_{t+1}) in registers and stream results out with evict-first stores.
+// HBM traffic = algorithmic: fwd 12 B/step, bwd 12 B/step (+ one extra value row).
+//
+// Arithmetic uses explicit round-to-nearest intrinsics in origin's operation order (no FMA
+// contraction), so forward results are bit-identical to origin fp32 on CPU / oracle_f32.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "scan_pipe.cuh"
+
+namespace hpcrll {
+
+// ------------------------------------------------------------------------------------------------
+// d_t table (device, fp32, cached per (device, T, lambda)).  Built on the host in double exactly as
+// origin does (`denom = 1 + lambda_*denom` on Python floats, gae.py:34) and rounded once to fp32.
+// Padded with 1.0 to a multiple of 64 rows so every ring stage can bulk-copy a full slice.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct DtabKey {
+    int dev;
+    int64_t T;
+    uint64_t lam_bits;
+    bool operator<(const DtabKey& o) const {
+        if (dev != o.dev) return dev < o.dev;
+        if (T != o.T) return T < o.T;
+        return lam_bits < o.lam_bits;
+    }
+};
+std::mutex g_dtab_mu;
+std::map<DtabKey, float*> g_dtab;
+constexpr int kDtabPad = 64;
+}  // namespace
+
+static int get_dtab(int64_t T, double lambda, const float** out) {
+    int dev = 0;
+    HPC_CUDA(cudaGetDevice(&dev));
+    DtabKey key{dev, T, 0};
+    std::memcpy(&key.lam_bits, &lambda, sizeof(double));
+    std::lock_guard<std::mutex> lk(g_dtab_mu);
+    auto it = g_dtab.find(key);
+    if (it != g_dtab.end()) {
+        *out = it->second;
+        return HPC_RLL_OK;
+    }
+    if (g_dtab.size() >= 256) {  // rare: bound the cache; entries may still be in use -> drain first
+        HPC_CUDA(cudaDeviceSynchronize());
+        for (auto& kv : g_dtab) cudaFree(kv.second);
+        g_dtab.clear();
+    }
+    const int64_t padded = ((T + kDtabPad - 1) / kDtabPad) * kDtabPad + kDtabPad;
+    std::vector<float> h(static_cast<size_t>(padded), 1.0f);
+    double den = 0.0;
+    for (int64_t t = T - 1; t >= 0; --t) {
+        den = 1.0 + lambda * den;
+        h[static_cast<size_t>(t)] = static_cast<float>(den);
+    }
+    float* d = nullptr;
+    HPC_CUDA(cudaMalloc(&d, sizeof(float) * static_cast<size_t>(padded)));
+    // blocking copy: the table is valid for every stream once this returns (first use per (T,lambda)
+    // only; do one warm-up call before CUDA-graph capture)
+    cudaError_t e = cudaMemcpy(d, h.data(), sizeof(float) * static_cast<size_t>(padded), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return set_error(HPC_RLL_ECUDA, "gae: uploading d_t table failed: %s", cudaGetErrorString(e));
+    }
+    g_dtab[key] = d;
+    *out = d;
+    return HPC_RLL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct GaeFwdBody {
+    float g, v1, gamma, factor;
+    float* adv;  // running pointer: &adv[t][col] of the NEXT step (steps arrive with t descending)
+    int64_t ld;
+    bool valid;
+    __device__ __forceinline__ void step(int /*t*/, const float (&x)[2], float d) {
+        // x[0] = v_t, x[1] = r_t
+        const float delta = __fsub_rn(__fadd_rn(x[1], __fmul_rn(gamma, v1)), x[0]);
+        g = __fadd_rn(__fmul_rn(d, delta), __fmul_rn(factor, g));
+        if (valid) st_stream(adv, __fdiv_rn(g, d));
+        adv -= ld;
+        v1 = x[0];
+    }
+};
+
+template <int BT, int TT, int ST>
+__global__ void __launch_bounds__(BT + 32) gae_fwd_tma(const __grid_constant__ TmapPack<2> maps,
+                                                        const float* __restrict__ dtab,
+                                                        const float* __restrict__ value, int64_t ld_value,
+                                                        float* __restrict__ adv, int64_t ld_adv, int T, int B,
+                                                        float gamma, float factor) {
+    using Pipe = ScanPipe<2, BT, TT, ST, true>;
+    const int col0 = blockIdx.x * BT;
+    const int col = col0 + threadIdx.x;
+    GaeFwdBody body;
+    body.valid = threadIdx.x < BT && col < B;
+    body.g = 0.f;
+    body.gamma = gamma;
+    body.factor = factor;
+    body.ld = ld_adv;
+    body.adv = adv + static_cast<int64_t>(T - 1) * ld_adv + col;
+    body.v1 = body.valid ? __ldg(value + static_cast<int64_t>(T) * ld_value + col) : 0.f;
+    Pipe::template run<true>(maps, dtab, T, col0, body);
+}
+
+struct GaeBwdBody {
+    float gh, prev, gamma, factor;
+    float* gv;
+    float* gr;
+    int64_t ld_gv, ld_gr;
+    bool valid;
+    // gv / gr are running pointers (&grad[t][col] of the next step; t ascending)
+    __device__ __forceinline__ void step(int /*t*/, const float (&x)[1], float d) {
+        const float h = __fadd_rn(__fdiv_rn(x[0], d), __fmul_rn(factor, gh));
+        gh = h;
+        const float dd = __fmul_rn(d, h);
+        if (valid) {
+            st_stream(gr, dd);
+            st_stream(gv, __fsub_rn(__fmul_rn(gamma, prev), dd));
+        }
+        gr += ld_gr;
+        gv += ld_gv;
+        prev = dd;
+    }
+};
+
+template <int BT, int TT, int ST>
+__global__ void __launch_bounds__(BT + 32) gae_bwd_tma(const __grid_constant__ TmapPack<1> maps,
+                                                        const float* __restrict__ dtab,
+                                                        float* __restrict__ grad_value, int64_t ld_gv,
+                                                        float* __restrict__ grad_reward, int64_t ld_gr, int T, int B,
+                                                        float gamma, float factor) {
+    using Pipe = ScanPipe<1, BT, TT, ST, true>;
+    const int col0 = blockIdx.x * BT;
+    const int col = col0 + threadIdx.x;
+    GaeBwdBody body;
+    body.valid = threadIdx.x < BT && col < B;
+    body.gh = 0.f;
+    body.prev = 0.f;
+    body.gamma = gamma;
+    body.factor = factor;
+    body.gv = grad_value + col;
+    body.gr = grad_reward + col;
+    body.ld_gv = ld_gv;
+    body.ld_gr = ld_gr;
+    Pipe::template run<false>(maps, dtab, T, col0, body);
+    if (body.valid) st_stream(body.gv, __fmul_rn(gamma, body.prev));  // row T
+}
+
+// Generic (no alignment requirements) variants: one thread per column, plain coalesced loads with
+// a 4-deep software prefetch.  Used when a pointer / pitch is not 16-byte aligned so TMA cannot
+// describe the tensor.  Still a CUDA kernel -- there is no CPU path.
+__global__ void __launch_bounds__(128) gae_fwd_generic(const float* __restrict__ value, int64_t ld_value,
+                                                        const float* __restrict__ reward, int64_t ld_reward,
+                                                        const float* __restrict__ dtab, float* __restrict__ adv,
+                                                        int64_t ld_adv, int T, int B, float gamma, float factor) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= B) return;
+    GaeFwdBody body;
+    body.valid = true;
+    body.g = 0.f;
+    body.gamma = gamma;
+    body.factor = factor;
+    body.ld = ld_adv;
+    body.adv = adv + static_cast<int64_t>(T - 1) * ld_adv + col;
+    body.v1 = value[static_cast<int64_t>(T) * ld_value + col];
+    constexpr int U = 8;
+    int t = T - 1;
+    for (; t >= U - 1; t -= U) {
+        float v[U], r[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            v[u] = ld_stream(value + static_cast<int64_t>(t - u) * ld_value + col);
+            r[u] = ld_stream(reward + static_cast<int64_t>(t - u) * ld_reward + col);
+            d[u] = __ldg(dtab + t - u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float x[2] = {v[u], r[u]};
+            body.step(t - u, x, d[u]);
+        }
+    }
+    for (; t >= 0; --t) {
+        const float x[2] = {value[static_cast<int64_t>(t) * ld_value + col],
+                            reward[static_cast<int64_t>(t) * ld_reward + col]};
+        body.step(t, x, __ldg(dtab + t));
+    }
+}
+
+__global__ void __launch_bounds__(128) gae_bwd_generic(const float* __restrict__ grad_adv, int64_t ld_ga,
+                                                        const float* __restrict__ dtab,
+                                                        float* __restrict__ grad_value, int64_t ld_gv,
+                                                        float* __restrict__ grad_reward, int64_t ld_gr, int T, int B,
+                                                        float gamma, float factor) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= B) return;
+    GaeBwdBody body;
+    body.valid = true;
+    body.gh = 0.f;
+    body.prev = 0.f;
+    body.gamma = gamma;
+    body.factor = factor;
+    body.gv = grad_value + col;
+    body.gr = grad_reward + col;
+    body.ld_gv = ld_gv;
+    body.ld_gr = ld_gr;
+    constexpr int U = 8;
+    int t = 0;
+    for (; t + U <= T; t += U) {
+        float g[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            g[u] = ld_stream(grad_adv + static_cast<int64_t>(t + u) * ld_ga + col);
+            d[u] = __ldg(dtab + t + u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float x[1] = {g[u]};
+            body.step(t + u, x, d[u]);
+        }
+    }
+    for (; t < T; ++t) {
+        const float x[1] = {grad_adv[static_cast<int64_t>(t) * ld_ga + col]};
+        body.step(t, x, __ldg(dtab + t));
+    }
+    *body.gv = __fmul_rn(gamma, body.prev);  // row T
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+
+template <int BT, int TT, int ST>
+static int launch_fwd_tma(const float* value, int64_t ldv, const float* reward, int64_t ldr, const float* dtab,
+                          float* adv, int64_t lda, int64_t T, int64_t B, float gamma, float factor,
+                          cudaStream_t stream) {
+    using Pipe = ScanPipe<2, BT, TT, ST, true>;
+    static SmemOptIn opt;
+    auto kernel = gae_fwd_tma<BT, TT, ST>;
+    if (int rc0 = opt.ensure(kernel, Pipe::kSmemBytes)) return rc0;
+    TmapPack<2> maps;
+    int rc = make_tmap_2d(&maps.m[0], value, T + 1, B, ldv, TT, BT);
+    if (rc) return rc;
+    rc = make_tmap_2d(&maps.m[1], reward, T, B, ldr, TT, BT);
+    if (rc) return rc;
+    const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
+    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, dtab, value, ldv, adv, lda,
+                                                              static_cast<int>(T), static_cast<int>(B), gamma, factor);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+template <int BT, int TT, int ST>
+static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab, float* gv, int64_t ldgv, float* gr,
+                          int64_t ldgr, int64_t T, int64_t B, float gamma, float factor, cudaStream_t stream) {
+    using Pipe = ScanPipe<1, BT, TT, ST, true>;
+    static SmemOptIn opt;
+    auto kernel = gae_bwd_tma<BT, TT, ST>;
+    if (int rc0 = opt.ensure(kernel, Pipe::kSmemBytes)) return rc0;
+    TmapPack<1> maps;
+    int rc = make_tmap_2d(&maps.m[0], grad_adv, T, B, ldg, TT, BT);
+    if (rc) return rc;
+    const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
+    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, dtab, gv, ldgv, gr, ldgr, static_cast<int>(T),
+                                                              static_cast<int>(B), gamma, factor);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+// configuration table (index = hpc_rll_debug_set_config(HPC_RLL_OP_GAE, i)); -1/auto picks by B.
+//   0: BT=64  TT=16 ST=3      1: BT=128 TT=16 ST=3     2: BT=32 TT=32 ST=3
+//   3: BT=64  TT=32 ST=3      4: BT=128 TT=8  ST=4     5: BT=64 TT=8  ST=6
+//   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     99: generic (non-TMA) kernel
+static int pick_cfg(int64_t B) {
+    const int forced = tuning_config(HPC_RLL_OP_GAE);
+    if (forced >= 0) return forced;
+    const int64_t sms = sm_count();
+    if (B >= 128 * 3 * sms) return 1;
+    if (B >= 64 * 2 * sms) return 0;
+    return 2;
+}
+
+static int gae_forward_impl(const float* value, int64_t ldv, const float* reward, int64_t ldr, float* adv,
+                            int64_t lda, int64_t T, int64_t B, double gamma, double lambda, cudaStream_t stream) {
+    HPC_REQUIRE(T >= 0 && B >= 0, "gae_forward: negative size T=%lld B=%lld", (long long)T, (long long)B);
+    if (T == 0 || B == 0) return HPC_RLL_OK;
+    HPC_REQUIRE(value && reward && adv, "gae_forward: null pointer");
+    HPC_REQUIRE(ldv >= B && ldr >= B && lda >= B, "gae_forward: row pitch smaller than B");
+    HPC_REQUIRE(T < (int64_t(1) << 31) - 64 && B < (int64_t(1) << 31) - 512, "gae_forward: T/B exceed 2^31");
+    const float* dtab = nullptr;
+    int rc = get_dtab(T, lambda, &dtab);
+    if (rc) return rc;
+    const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
+    int cfg = pick_cfg(B);
+    const bool tma = tma_ok_2d(value, B, ldv) && tma_ok_2d(reward, B, ldr);
+    if (!tma) cfg = 99;
+    switch (cfg) {
+        case 0: return launch_fwd_tma<64, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 1: return launch_fwd_tma<128, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 2: return launch_fwd_tma<32, 32, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 3: return launch_fwd_tma<64, 32, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 4: return launch_fwd_tma<128, 8, 4>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 5: return launch_fwd_tma<64, 8, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 6: return launch_fwd_tma<128, 32, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 7: return launch_fwd_tma<256, 8, 4>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        default: break;
+    }
+    const unsigned grid = static_cast<unsigned>((B + 127) / 128);
+    gae_fwd_generic<<<grid, 128, 0, stream>>>(value, ldv, reward, ldr, dtab, adv, lda, static_cast<int>(T),
+                                              static_cast<int>(B), g, f);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int64_t ldgv, float* gr, int64_t ldgr,
+                             int64_t T, int64_t B, double gamma, double lambda, cudaStream_t stream) {
+    HPC_REQUIRE(T >= 0 && B >= 0, "gae_backward: negative size T=%lld B=%lld", (long long)T, (long long)B);
+    if (B == 0) return HPC_RLL_OK;
+    HPC_REQUIRE(gv != nullptr, "gae_backward: null grad_value");
+    if (T == 0) {  // value is (1,B): no advantage depends on it
+        HPC_CUDA(cudaMemsetAsync(gv, 0, sizeof(float) * static_cast<size_t>(B), stream));
+        return HPC_RLL_OK;
+    }
+    HPC_REQUIRE(grad_adv && gr, "gae_backward: null pointer");
+    HPC_REQUIRE(ldg >= B && ldgv >= B && ldgr >= B, "gae_backward: row pitch smaller than B");
+    HPC_REQUIRE(T < (int64_t(1) << 31) - 64 && B < (int64_t(1) << 31) - 512, "gae_backward: T/B exceed 2^31");
+    const float* dtab = nullptr;
+    int rc = get_dtab(T, lambda, &dtab);
+    if (rc) return rc;
+    const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
+    int cfg = pick_cfg(B);
+    if (!tma_ok_2d(grad_adv, B, ldg)) cfg = 99;
+    switch (cfg) {
+        case 0: return launch_bwd_tma<64, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 1: return launch_bwd_tma<128, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 2: return launch_bwd_tma<32, 32, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 3: return launch_bwd_tma<64, 32, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 4: return launch_bwd_tma<128, 8, 4>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 5: return launch_bwd_tma<64, 8, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 6: return launch_bwd_tma<128, 32, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 7: return launch_bwd_tma<256, 8, 4>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        default: break;
+    }
+    const unsigned grid = static_cast<unsigned>((B + 127) / 128);
+    gae_bwd_generic<<<grid, 128, 0, stream>>>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, static_cast<int>(T),
+                                              static_cast<int>(B), g, f);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer end-to-end path: column blocks pipelined over H2D / kernels / D2H
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct HostPipe {
+    static constexpr int kSlots = 3;
+    int dev = -1;
+    cudaStream_t stream[kSlots] = {};
+    float* buf[kSlots] = {};
+    size_t cap = 0;  // floats per slot
+    std::mutex mu;
+};
+HostPipe g_hp;
+}  // namespace
+
+static int gae_host_impl(const float* h_value, const float* h_reward, const float* h_gadv, float* h_adv,
+                         float* h_gvalue, float* h_greward, int64_t T, int64_t B, double gamma, double lambda) {
+    HPC_REQUIRE(T > 0 && B > 0, "gae_fwd_bwd_host: T and B must be positive");
+    HPC_REQUIRE(h_value && h_reward && h_adv, "gae_fwd_bwd_host: null forward buffer");
+    const bool bwd = h_gadv != nullptr;
+    HPC_REQUIRE(!bwd || (h_gvalue && h_greward), "gae_fwd_bwd_host: backward needs grad_value and grad_reward");
+    std::lock_guard<std::mutex> lk(g_hp.mu);
+    int dev = 0;
+    HPC_CUDA(cudaGetDevice(&dev));
+    // column block: multiple of 128 columns, ~16 MB per tensor per slot
+    int64_t cb = (int64_t(4) << 20) / (T + 1);
+    cb = (cb / 128) * 128;
+    if (cb < 128) cb = 128;
+    if (cb > B) cb = ((B + 3) / 4) * 4;
+    const size_t rows = static_cast<size_t>(T + 1);
+    const size_t per_tensor = rows * static_cast<size_t>(cb);
+    const size_t need = per_tensor * 6;
+    if (g_hp.dev != dev || g_hp.cap < need) {
+        for (int s = 0; s < HostPipe::kSlots; ++s) {
+            if (g_hp.buf[s]) cudaFree(g_hp.buf[s]);
+            g_hp.buf[s] = nullptr;
+            if (g_hp.dev != dev && g_hp.stream[s]) {
+                cudaStreamDestroy(g_hp.stream[s]);
+                g_hp.stream[s] = nullptr;
+            }
+        }
+        g_hp.cap = 0;
+        for (int s = 0; s < HostPipe::kSlots; ++s) {
+            if (!g_hp.stream[s]) HPC_CUDA(cudaStreamCreateWithFlags(&g_hp.stream[s], cudaStreamNonBlocking));
+            HPC_CUDA(cudaMalloc(&g_hp.buf[s], need * sizeof(float)));
+        }
+        g_hp.cap = need;
+        g_hp.dev = dev;
+    }
+    const size_t hp = static_cast<size_t>(B) * sizeof(float);  // host pitch
+    const size_t dp = static_cast<size_t>(cb) * sizeof(float); // device pitch
+    int slot = 0;
+    for (int64_t c0 = 0; c0 < B; c0 += cb, slot = (slot + 1) % HostPipe::kSlots) {
+        const int64_t w = (B - c0 < cb) ? (B - c0) : cb;
+        const size_t wb = static_cast<size_t>(w) * sizeof(float);
+        cudaStream_t st = g_hp.stream[slot];
+        float* d_value = g_hp.buf[slot];
+        float* d_reward = d_value + per_tensor;
+        float* d_adv = d_reward + per_tensor;
+        float* d_gadv = d_adv + per_tensor;
+        float* d_gvalue = d_gadv + per_tensor;
+        float* d_greward = d_gvalue + per_tensor;
+        HPC_CUDA(cudaMemcpy2DAsync(d_value, dp, h_value + c0, hp, wb, rows, cudaMemcpyHostToDevice, st));
+        HPC_CUDA(cudaMemcpy2DAsync(d_reward, dp, h_reward + c0, hp, wb, rows - 1, cudaMemcpyHostToDevice, st));
+        int rc = gae_forward_impl(d_value, cb, d_reward, cb, d_adv, cb, T, w, gamma, lambda, st);
+        if (rc) return rc;
+        HPC_CUDA(cudaMemcpy2DAsync(h_adv + c0, hp, d_adv, dp, wb, rows - 1, cudaMemcpyDeviceToHost, st));
+        if (bwd) {
+            HPC_CUDA(cudaMemcpy2DAsync(d_gadv, dp, h_gadv + c0, hp, wb, rows - 1, cudaMemcpyHostToDevice, st));
+            rc = gae_backward_impl(d_gadv, cb, d_gvalue, cb, d_greward, cb, T, w, gamma, lambda, st);
+            if (rc) return rc;
+            HPC_CUDA(cudaMemcpy2DAsync(h_gvalue + c0, hp, d_gvalue, dp, wb, rows, cudaMemcpyDeviceToHost, st));
+            HPC_CUDA(cudaMemcpy2DAsync(h_greward + c0, hp, d_greward, dp, wb, rows - 1, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int s = 0; s < HostPipe::kSlots; ++s) HPC_CUDA(cudaStreamSynchronize(g_hp.stream[s]));
+    return HPC_RLL_OK;
+}
+
+}  // namespace hpcrll
+
+extern "C" {
+
+int hpc_rll_gae_forward(const float* value, const float* reward, float* adv, int64_t T, int64_t B, double gamma,
+                        double lambda, void* stream) {
+    return hpcrll::gae_forward_impl(value, B, reward, B, adv, B, T, B, gamma, lambda, hpcrll::as_stream(stream));
+}
+
+int hpc_rll_gae_backward(const float* grad_adv, float* grad_value, float* grad_reward, int64_t T, int64_t B,
+                         double gamma, double lambda, void* stream) {
+    return hpcrll::gae_backward_impl(grad_adv, B, grad_value, B, grad_reward, B, T, B, gamma, lambda,
+                                     hpcrll::as_stream(stream));
+}
+
+int hpc_rll_gae_forward_ld(const float* value, int64_t ld_value, const float* reward, int64_t ld_reward,
+                           float* adv, int64_t ld_adv, int64_t T, int64_t B, double gamma, double lambda,
+                           void* stream) {
+    return hpcrll::gae_forward_impl(value, ld_value, reward, ld_reward, adv, ld_adv, T, B, gamma, lambda,
+                                    hpcrll::as_stream(stream));
+}
+
+int hpc_rll_gae_backward_ld(const float* grad_adv, int64_t ld_grad_adv, float* grad_value, int64_t ld_grad_value,
+                            float* grad_reward, int64_t ld_grad_reward, int64_t T, int64_t B, double gamma,
+                            double lambda, void* stream) {
+    return hpcrll::gae_backward_impl(grad_adv, ld_grad_adv, grad_value, ld_grad_value, grad_reward, ld_grad_reward,
+                                     T, B, gamma, lambda, hpcrll::as_stream(stream));
+}
+
+int hpc_rll_gae_fwd_bwd_host(const float* h_value, const float* h_reward, const float* h_grad_adv, float* h_adv,
+                             float* h_grad_value, float* h_grad_reward, int64_t T, int64_t B, double gamma,
+                             double lambda) {
+    return hpcrll::gae_host_impl(h_value, h_reward, h_grad_adv, h_adv, h_grad_value, h_grad_reward, T, B, gamma,
+                                 lambda);
+}
+
+}  // extern "C"

@@ -1,0 +1,148 @@
+"""GAE parity on the GPU: CUDA kernels (through libhpc_rll_b200.so) vs the oracle / golden fixtures.
+
+Tolerances: forward and backward are element-wise chains evaluated in the oracle's exact fp32
+operation order, so both must be BIT-EXACT against oracle_f32 (and the forward against origin's
+own fp32 output in the golden fixtures).  Gradients vs origin autograd (different summation
+structure): 1e-5 norm-relative (north_star tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests._golden import Case, names, rel_err
+from tests._gpu import dev, host, need_cuda, rng
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(1024, 64), (128, 128), (1, 5), (37, 3), (100, 260), (17, 1028), (64, 1), (33, 4), (250, 4096),
+          (16, 128), (15, 132)]
+
+
+def _run(value, reward, grad_adv, gamma, lam):
+    from di_hpc_b200.rl_utils.gae import GAE
+    v = dev(value).requires_grad_(True)
+    r = dev(reward).requires_grad_(True)
+    adv = GAE(*reward.shape)(v, r, gamma, lam)
+    adv.backward(dev(grad_adv))
+    torch.cuda.synchronize()
+    return host(adv), host(v.grad), host(r.grad)
+
+
+@pytest.mark.parametrize("T,B", SHAPES)
+def test_gae_vs_oracle_bitexact(T, B):
+    need_cuda()
+    g = rng(T * 100003 + B)
+    value = g.standard_normal((T + 1, B), dtype=np.float32)
+    reward = g.standard_normal((T, B), dtype=np.float32)
+    gadv = g.standard_normal((T, B), dtype=np.float32)
+    adv, gv, gr = _run(value, reward, gadv, 0.99, 0.97)
+    assert np.array_equal(adv, orc.gae_forward(value, reward, 0.99, 0.97))
+    ob = orc.gae_backward(gadv, 0.99, 0.97)
+    assert np.array_equal(gv, ob["value"])
+    assert np.array_equal(gr, ob["reward"])
+
+
+@pytest.mark.parametrize("name", names("gae"))
+def test_gae_vs_golden(name):
+    need_cuda()
+    c = Case(name)
+    adv, gv, gr = _run(c.inp("value"), c.inp("reward"), c.inp("grad_adv"), c.attr("gamma"), c.attr("lambda_"))
+    assert np.array_equal(adv, c.out("adv", 32)), "forward must be bit-exact vs origin fp32"
+    assert rel_err(gv, c.grad("value", 32)) <= 1e-5
+    assert rel_err(gr, c.grad("reward", 32)) <= 1e-5
+    assert rel_err(gv, c.grad("value", 64)) <= 1e-5
+    assert rel_err(gr, c.grad("reward", 64)) <= 1e-5
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 99])
+def test_gae_every_kernel_config(cfg):
+    """All tile configurations (and the non-TMA kernel) must give identical bits."""
+    need_cuda()
+    from di_hpc_b200 import _abi
+    g = rng(77 + cfg)
+    T, B = 203, 1300
+    value = g.standard_normal((T + 1, B), dtype=np.float32)
+    reward = g.standard_normal((T, B), dtype=np.float32)
+    gadv = g.standard_normal((T, B), dtype=np.float32)
+    try:
+        _abi.set_config(0, cfg)
+        adv, gv, gr = _run(value, reward, gadv, 0.95, 0.9)
+    finally:
+        _abi.set_config(0, -1)
+    assert np.array_equal(adv, orc.gae_forward(value, reward, 0.95, 0.9))
+    ob = orc.gae_backward(gadv, 0.95, 0.9)
+    assert np.array_equal(gv, ob["value"]) and np.array_equal(gr, ob["reward"])
+
+
+def test_gae_strided_views():
+    """_ld entry points: operate on column slices of wider buffers without copying."""
+    need_cuda()
+    from di_hpc_b200 import _abi
+    g = rng(5)
+    T, B, LD, C0 = 50, 96, 256, 64
+    big_v = dev(g.standard_normal((T + 1, LD), dtype=np.float32))
+    big_r = dev(g.standard_normal((T, LD), dtype=np.float32))
+    big_a = torch.zeros((T, LD), device="cuda")
+    L = _abi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    _abi.check(L.hpc_rll_gae_forward_ld(big_v[:, C0:].data_ptr(), LD, big_r[:, C0:].data_ptr(), LD,
+                                        big_a[:, C0:].data_ptr(), LD, T, B, 0.99, 0.97, st), "fwd_ld")
+    torch.cuda.synchronize()
+    want = orc.gae_forward(host(big_v[:, C0:C0 + B]).copy(), host(big_r[:, C0:C0 + B]).copy(), 0.99, 0.97)
+    assert np.array_equal(host(big_a[:, C0:C0 + B]), want)
+    assert float(big_a[:, :C0].abs().max()) == 0.0 and float(big_a[:, C0 + B:].abs().max()) == 0.0
+
+
+def test_gae_full_size_properties():
+    """BASELINE C1 size (T=1024, B=65536): adjoint identity <adv(v,r),G> == <v,gv>+<r,gr> (GAE is linear),
+    and exact agreement with the oracle on column slabs (columns are independent)."""
+    need_cuda()
+    from di_hpc_b200.rl_utils.gae import GAE
+    T, B = 1024, 65536
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    v = torch.randn(T + 1, B, device="cuda", generator=gen).requires_grad_(True)
+    r = torch.randn(T, B, device="cuda", generator=gen).requires_grad_(True)
+    G = torch.randn(T, B, device="cuda", generator=gen)
+    adv = GAE(T, B)(v, r)
+    adv.backward(G)
+    lhs = (adv.detach().double() * G.double()).sum().item()
+    rhs = (v.detach().double() * v.grad.double()).sum().item() + (r.detach().double() * r.grad.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(1.0, abs(lhs)), (lhs, rhs)
+    for sl in (slice(0, 192), slice(32700, 32900), slice(B - 130, B)):
+        vs, rs, gs = host(v[:, sl]).copy(), host(r[:, sl]).copy(), host(G[:, sl]).copy()
+        assert np.array_equal(host(adv[:, sl]), orc.gae_forward(vs, rs))
+        ob = orc.gae_backward(gs)
+        assert np.array_equal(host(v.grad[:, sl]), ob["value"])
+        assert np.array_equal(host(r.grad[:, sl]), ob["reward"])
+
+
+def test_gae_host_entry_matches_device_path():
+    """hpc_rll_gae_fwd_bwd_host (pinned host buffers, chunked H2D/compute/D2H pipeline)."""
+    need_cuda()
+    from di_hpc_b200 import _abi
+    g = rng(11)
+    T, B = 257, 9000
+    value = torch.from_numpy(g.standard_normal((T + 1, B), dtype=np.float32)).pin_memory()
+    reward = torch.from_numpy(g.standard_normal((T, B), dtype=np.float32)).pin_memory()
+    gadv = torch.from_numpy(g.standard_normal((T, B), dtype=np.float32)).pin_memory()
+    adv = torch.empty((T, B)).pin_memory()
+    gv = torch.empty((T + 1, B)).pin_memory()
+    gr = torch.empty((T, B)).pin_memory()
+    _abi.check(_abi.lib().hpc_rll_gae_fwd_bwd_host(value.data_ptr(), reward.data_ptr(), gadv.data_ptr(),
+                                                   adv.data_ptr(), gv.data_ptr(), gr.data_ptr(), T, B, 0.99, 0.97),
+               "gae_fwd_bwd_host")
+    assert np.array_equal(adv.numpy(), orc.gae_forward(value.numpy(), reward.numpy()))
+    ob = orc.gae_backward(gadv.numpy())
+    assert np.array_equal(gv.numpy(), ob["value"]) and np.array_equal(gr.numpy(), ob["reward"])
+
+
+def test_gae_argument_errors():
+    need_cuda()
+    from di_hpc_b200 import _abi
+    from di_hpc_b200.rl_utils.gae import GAE
+    with pytest.raises(ValueError):
+        GAE(4, 4)(torch.zeros(4, 4, device="cuda"), torch.zeros(4, 4, device="cuda"))
+    with pytest.raises(TypeError):
+        GAE(4, 4)(torch.zeros(5, 4, device="cuda", dtype=torch.float64), torch.zeros(4, 4, device="cuda"))
+    rc = _abi.lib().hpc_rll_gae_forward(None, None, None, 4, 4, 0.99, 0.97, None)
+    assert rc == 1 and b"null" in _abi.lib().hpc_rll_last_error()
