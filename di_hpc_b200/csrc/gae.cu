@@ -20,6 +20,11 @@
 //
 // Arithmetic uses explicit round-to-nearest intrinsics in origin's operation order (no FMA
 // contraction), so forward results are bit-identical to origin fp32 on CPU / oracle_f32.
+// The division by d_t uses the table's correctly rounded reciprocal r_t = RN(1/d_t) and one FMA
+// residual step (q0 = x*r; q = fma(fma(-d,q0,x), r, q0)) -- by Markstein's theorem this is the
+// correctly rounded quotient for every normal-range x (brute-forced on 1.5e8 cases, see
+// DESIGN.md); it costs 3 instructions instead of the ~14 of the generic IEEE division sequence.
+// Non-finite x yields NaN (IEEE division would give +-inf for x = +-inf).
 #include <cmath>
 #include <cstring>
 #include <map>
@@ -33,7 +38,8 @@ namespace hpcrll {
 // ------------------------------------------------------------------------------------------------
 // d_t table (device, fp32, cached per (device, T, lambda)).  Built on the host in double exactly as
 // origin does (`denom = 1 + lambda_*denom` on Python floats, gae.py:34) and rounded once to fp32.
-// Padded with 1.0 to a multiple of 64 rows so every ring stage can bulk-copy a full slice.
+// Stored as interleaved pairs (d_t, RN(1/d_t)); padded with (1,1) to a multiple of 64 rows so every
+// ring stage can bulk-copy a full slice.
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct DtabKey {
@@ -68,17 +74,19 @@ static int get_dtab(int64_t T, double lambda, const float** out) {
         g_dtab.clear();
     }
     const int64_t padded = ((T + kDtabPad - 1) / kDtabPad) * kDtabPad + kDtabPad;
-    std::vector<float> h(static_cast<size_t>(padded), 1.0f);
+    std::vector<float> h(static_cast<size_t>(padded) * 2, 1.0f);
     double den = 0.0;
     for (int64_t t = T - 1; t >= 0; --t) {
         den = 1.0 + lambda * den;
-        h[static_cast<size_t>(t)] = static_cast<float>(den);
+        const float df = static_cast<float>(den);
+        h[static_cast<size_t>(t) * 2] = df;
+        h[static_cast<size_t>(t) * 2 + 1] = 1.0f / df;  // host fp32 division: correctly rounded
     }
     float* d = nullptr;
-    HPC_CUDA(cudaMalloc(&d, sizeof(float) * static_cast<size_t>(padded)));
+    HPC_CUDA(cudaMalloc(&d, sizeof(float) * h.size()));
     // blocking copy: the table is valid for every stream once this returns (first use per (T,lambda)
     // only; do one warm-up call before CUDA-graph capture)
-    cudaError_t e = cudaMemcpy(d, h.data(), sizeof(float) * static_cast<size_t>(padded), cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(d, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         cudaFree(d);
         return set_error(HPC_RLL_ECUDA, "gae: uploading d_t table failed: %s", cudaGetErrorString(e));
@@ -91,16 +99,22 @@ static int get_dtab(int64_t T, double lambda, const float** out) {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
+// correctly rounded x/d given r = RN(1/d) (see file header)
+__device__ __forceinline__ float div_by_table(float x, float d, float r) {
+    const float q0 = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-d, q0, x), r, q0);
+}
+
 struct GaeFwdBody {
     float g, v1, gamma, factor;
     float* adv;  // running pointer: &adv[t][col] of the NEXT step (steps arrive with t descending)
     int64_t ld;
     bool valid;
-    __device__ __forceinline__ void step(int /*t*/, const float (&x)[2], float d) {
-        // x[0] = v_t, x[1] = r_t
+    __device__ __forceinline__ void step(int /*t*/, const float (&x)[2], const float (&dt)[2]) {
+        // x[0] = v_t, x[1] = r_t, dt = (d_t, 1/d_t)
         const float delta = __fsub_rn(__fadd_rn(x[1], __fmul_rn(gamma, v1)), x[0]);
-        g = __fadd_rn(__fmul_rn(d, delta), __fmul_rn(factor, g));
-        if (valid) st_stream(adv, __fdiv_rn(g, d));
+        g = __fadd_rn(__fmul_rn(dt[0], delta), __fmul_rn(factor, g));
+        if (valid) st_stream(adv, div_by_table(g, dt[0], dt[1]));
         adv -= ld;
         v1 = x[0];
     }
@@ -112,7 +126,7 @@ __global__ void __launch_bounds__(BT + 32) gae_fwd_tma(const __grid_constant__ T
                                                         const float* __restrict__ value, int64_t ld_value,
                                                         float* __restrict__ adv, int64_t ld_adv, int T, int B,
                                                         float gamma, float factor) {
-    using Pipe = ScanPipe<2, BT, TT, ST, true>;
+    using Pipe = ScanPipe<2, BT, TT, ST, 2>;
     const int col0 = blockIdx.x * BT;
     const int col = col0 + threadIdx.x;
     GaeFwdBody body;
@@ -133,10 +147,10 @@ struct GaeBwdBody {
     int64_t ld_gv, ld_gr;
     bool valid;
     // gv / gr are running pointers (&grad[t][col] of the next step; t ascending)
-    __device__ __forceinline__ void step(int /*t*/, const float (&x)[1], float d) {
-        const float h = __fadd_rn(__fdiv_rn(x[0], d), __fmul_rn(factor, gh));
+    __device__ __forceinline__ void step(int /*t*/, const float (&x)[1], const float (&dt)[2]) {
+        const float h = __fadd_rn(div_by_table(x[0], dt[0], dt[1]), __fmul_rn(factor, gh));
         gh = h;
-        const float dd = __fmul_rn(d, h);
+        const float dd = __fmul_rn(dt[0], h);
         if (valid) {
             st_stream(gr, dd);
             st_stream(gv, __fsub_rn(__fmul_rn(gamma, prev), dd));
@@ -153,7 +167,7 @@ __global__ void __launch_bounds__(BT + 32) gae_bwd_tma(const __grid_constant__ T
                                                         float* __restrict__ grad_value, int64_t ld_gv,
                                                         float* __restrict__ grad_reward, int64_t ld_gr, int T, int B,
                                                         float gamma, float factor) {
-    using Pipe = ScanPipe<1, BT, TT, ST, true>;
+    using Pipe = ScanPipe<1, BT, TT, ST, 2>;
     const int col0 = blockIdx.x * BT;
     const int col = col0 + threadIdx.x;
     GaeBwdBody body;
@@ -190,23 +204,27 @@ __global__ void __launch_bounds__(128) gae_fwd_generic(const float* __restrict__
     constexpr int U = 8;
     int t = T - 1;
     for (; t >= U - 1; t -= U) {
-        float v[U], r[U], d[U];
+        float v[U], r[U];
+        float2 d[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             v[u] = ld_stream(value + static_cast<int64_t>(t - u) * ld_value + col);
             r[u] = ld_stream(reward + static_cast<int64_t>(t - u) * ld_reward + col);
-            d[u] = __ldg(dtab + t - u);
+            d[u] = __ldg(reinterpret_cast<const float2*>(dtab) + t - u);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float x[2] = {v[u], r[u]};
-            body.step(t - u, x, d[u]);
+            const float dt[2] = {d[u].x, d[u].y};
+            body.step(t - u, x, dt);
         }
     }
     for (; t >= 0; --t) {
         const float x[2] = {value[static_cast<int64_t>(t) * ld_value + col],
                             reward[static_cast<int64_t>(t) * ld_reward + col]};
-        body.step(t, x, __ldg(dtab + t));
+        const float2 d = __ldg(reinterpret_cast<const float2*>(dtab) + t);
+        const float dt[2] = {d.x, d.y};
+        body.step(t, x, dt);
     }
 }
 
@@ -230,21 +248,25 @@ __global__ void __launch_bounds__(128) gae_bwd_generic(const float* __restrict__
     constexpr int U = 8;
     int t = 0;
     for (; t + U <= T; t += U) {
-        float g[U], d[U];
+        float g[U];
+        float2 d[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             g[u] = ld_stream(grad_adv + static_cast<int64_t>(t + u) * ld_ga + col);
-            d[u] = __ldg(dtab + t + u);
+            d[u] = __ldg(reinterpret_cast<const float2*>(dtab) + t + u);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const float x[1] = {g[u]};
-            body.step(t + u, x, d[u]);
+            const float dt[2] = {d[u].x, d[u].y};
+            body.step(t + u, x, dt);
         }
     }
     for (; t < T; ++t) {
         const float x[1] = {grad_adv[static_cast<int64_t>(t) * ld_ga + col]};
-        body.step(t, x, __ldg(dtab + t));
+        const float2 d = __ldg(reinterpret_cast<const float2*>(dtab) + t);
+        const float dt[2] = {d.x, d.y};
+        body.step(t, x, dt);
     }
     *body.gv = __fmul_rn(gamma, body.prev);  // row T
 }
@@ -257,7 +279,7 @@ template <int BT, int TT, int ST>
 static int launch_fwd_tma(const float* value, int64_t ldv, const float* reward, int64_t ldr, const float* dtab,
                           float* adv, int64_t lda, int64_t T, int64_t B, float gamma, float factor,
                           cudaStream_t stream) {
-    using Pipe = ScanPipe<2, BT, TT, ST, true>;
+    using Pipe = ScanPipe<2, BT, TT, ST, 2>;
     static SmemOptIn opt;
     auto kernel = gae_fwd_tma<BT, TT, ST>;
     if (int rc0 = opt.ensure(kernel, Pipe::kSmemBytes)) return rc0;
@@ -277,7 +299,7 @@ static int launch_fwd_tma(const float* value, int64_t ldv, const float* reward, 
 template <int BT, int TT, int ST>
 static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab, float* gv, int64_t ldgv, float* gr,
                           int64_t ldgr, int64_t T, int64_t B, float gamma, float factor, cudaStream_t stream) {
-    using Pipe = ScanPipe<1, BT, TT, ST, true>;
+    using Pipe = ScanPipe<1, BT, TT, ST, 2>;
     static SmemOptIn opt;
     auto kernel = gae_bwd_tma<BT, TT, ST>;
     if (int rc0 = opt.ensure(kernel, Pipe::kSmemBytes)) return rc0;
@@ -295,13 +317,16 @@ static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab,
 // configuration table (index = hpc_rll_debug_set_config(HPC_RLL_OP_GAE, i)); -1/auto picks by B.
 //   0: BT=64  TT=16 ST=3      1: BT=128 TT=16 ST=3     2: BT=32 TT=32 ST=3
 //   3: BT=64  TT=32 ST=3      4: BT=128 TT=8  ST=4     5: BT=64 TT=8  ST=6
-//   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     99: generic (non-TMA) kernel
+//   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     8: BT=256 TT=16 ST=3
+//  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     99: generic (non-TMA) kernel
+// (a TMA box dimension is limited to 256 elements, so BT <= 256)
 static int pick_cfg(int64_t B) {
     const int forced = tuning_config(HPC_RLL_OP_GAE);
     if (forced >= 0) return forced;
     const int64_t sms = sm_count();
-    if (B >= 128 * 3 * sms) return 1;
-    if (B >= 64 * 2 * sms) return 0;
+    if (B >= 256 * sms) return 7;
+    if (B >= 128 * sms) return 1;
+    if (B >= 64 * sms) return 0;
     return 2;
 }
 
@@ -328,6 +353,9 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
         case 5: return launch_fwd_tma<64, 8, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         case 6: return launch_fwd_tma<128, 32, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         case 7: return launch_fwd_tma<256, 8, 4>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 8: return launch_fwd_tma<256, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 10: return launch_fwd_tma<256, 4, 8>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 11: return launch_fwd_tma<256, 8, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         default: break;
     }
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);
@@ -365,6 +393,9 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
         case 5: return launch_bwd_tma<64, 8, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         case 6: return launch_bwd_tma<128, 32, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         case 7: return launch_bwd_tma<256, 8, 4>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 8: return launch_bwd_tma<256, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 10: return launch_bwd_tma<256, 4, 8>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 11: return launch_bwd_tma<256, 8, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         default: break;
     }
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);

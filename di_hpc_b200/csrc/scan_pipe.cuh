@@ -6,7 +6,7 @@
 // tensors through an ST-deep shared-memory ring with cp.async.bulk.tensor (TMA) + mbarrier
 // expect-tx; BT consumer threads (one per column, bank-conflict-free row reads) walk the rows of
 // the box in scan order and carry the recurrence state in registers across boxes.  Optional
-// per-row constants (`rowtab`, e.g. GAE's denominators d_t) ride in the same stage as a 1-D bulk copy.
+// per-row constants (`rowtab`, e.g. GAE's denominators d_t and 1/d_t) ride in the same stage as a 1-D bulk copy.
 //
 //   * no thread ever issues a global load in the steady state: all input traffic is bulk async,
 //     ST-1 boxes per CTA are in flight while one is being consumed
@@ -26,21 +26,22 @@ struct TmapPack {
     CUtensorMap m[NIN];
 };
 
-template <int NIN, int BT, int TT, int ST, bool ROWTAB>
+template <int NIN, int BT, int TT, int ST, int NTAB>
 struct ScanPipe {
     static_assert(BT % 32 == 0, "column tile must be whole warps");
     static_assert(TT % 4 == 0, "row tile must keep the row table 16B aligned");
     static constexpr int kConsumerWarps = BT / 32;
     static constexpr int kThreads = BT + 32;  // + one producer warp
     static constexpr int kBoxBytes = TT * BT * 4;
-    static constexpr int kTabBytes = ROWTAB ? ((TT * 4 + 127) / 128) * 128 : 0;
+    static constexpr int kTabBytes = ((TT * NTAB * 4 + 127) / 128) * 128;  // NTAB fp32 constants per row
     static constexpr int kStageBytes = NIN * kBoxBytes + kTabBytes;
-    static constexpr uint32_t kTxBytes = NIN * kBoxBytes + (ROWTAB ? TT * 4 : 0);
+    static constexpr uint32_t kTxBytes = NIN * kBoxBytes + TT * NTAB * 4;
+    static constexpr int kTabN = NTAB > 0 ? NTAB : 1;
     static constexpr int kSmemBytes = ST * kStageBytes + 2 * ST * 8;
 
     // Runs the whole pipeline for the column tile starting at col0.
     //   body.step(t, x, rt): called by consumer thread c (column col0+c) for t in scan order,
-    //   x[k] = input k at (t, col0+c), rt = rowtab[t] (0 if !ROWTAB).
+    //   x[k] = input k at (t, col0+c), rt[k] = rowtab[t*NTAB + k] (per-row constants).
     template <bool REVERSE, class Body>
     static __device__ __forceinline__ void run(const TmapPack<NIN>& maps, const float* __restrict__ rowtab, int T,
                                                int col0, Body& body) {
@@ -77,7 +78,7 @@ struct ScanPipe {
                     mbar_arrive_expect_tx(&full[s], kTxBytes);
 #pragma unroll
                     for (int k = 0; k < NIN; ++k) tma_load_2d(st + k * kBoxBytes, &maps.m[k], col0, j * TT, &full[s]);
-                    if (ROWTAB) bulk_load_1d(st + NIN * kBoxBytes, rowtab + j * TT, TT * 4, &full[s]);
+                    if (NTAB > 0) bulk_load_1d(st + NIN * kBoxBytes, rowtab + j * TT * NTAB, TT * NTAB * 4, &full[s]);
                 }
             }
             return;
@@ -99,7 +100,10 @@ struct ScanPipe {
                     float x[NIN];
 #pragma unroll
                     for (int k = 0; k < NIN; ++k) x[k] = st[(k * TT + i) * BT + c];
-                    body.step(j * TT + i, x, ROWTAB ? tab[i] : 0.f);
+                    float rt[kTabN];
+#pragma unroll
+                    for (int k = 0; k < NTAB; ++k) rt[k] = tab[i * NTAB + k];
+                    body.step(j * TT + i, x, rt);
                 }
             } else {
                 for (int ii = 0; ii < rows; ++ii) {
@@ -107,7 +111,10 @@ struct ScanPipe {
                     float x[NIN];
 #pragma unroll
                     for (int k = 0; k < NIN; ++k) x[k] = st[(k * TT + i) * BT + c];
-                    body.step(j * TT + i, x, ROWTAB ? tab[i] : 0.f);
+                    float rt[kTabN];
+#pragma unroll
+                    for (int k = 0; k < NTAB; ++k) rt[k] = tab[i * NTAB + k];
+                    body.step(j * TT + i, x, rt);
                 }
             }
             __syncwarp();

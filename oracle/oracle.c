@@ -24,6 +24,7 @@
  * Loops over the independent batch axis are OpenMP-parallel (this is also the CPU baseline).
  */
 #include <math.h>
+#include <omp.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -123,30 +124,53 @@ static void gae_denoms(int64_t T, double lambda, real* d) {
     }
 }
 
+/* column range [b0,b1) of thread `tid` of `nt`: contiguous, 16-float aligned (streams well, vectorises) */
+static void col_range(int64_t B, int tid, int nt, int64_t* b0, int64_t* b1) {
+    int64_t chunk = ((B + nt - 1) / nt + 15) / 16 * 16;
+    *b0 = (int64_t)tid * chunk;
+    *b1 = *b0 + chunk;
+    if (*b0 > B) *b0 = B;
+    if (*b1 > B) *b1 = B;
+}
+
+/* parallel first-touch copy with the same thread->column mapping as the kernels below (NUMA placement
+ * for the CPU-baseline timing; not part of the algorithm) */
+void FN(orc_place_copy)(real* dst, const real* src, int64_t rows, int64_t B) {
+#pragma omp parallel
+    {
+        int64_t b0, b1;
+        col_range(B, omp_get_thread_num(), omp_get_num_threads(), &b0, &b1);
+        for (int64_t t = 0; t < rows; ++t)
+            for (int64_t b = b0; b < b1; ++b) dst[t * B + b] = src[t * B + b];
+    }
+}
+
 void FN(orc_gae_forward)(const real* value, const real* reward, real* adv, int64_t T, int64_t B, double gamma,
                          double lambda) {
     if (T <= 0 || B <= 0) return;
     real* d = (real*)malloc(sizeof(real) * (size_t)T);
     gae_denoms(T, lambda, d);
     const real g_r = (real)gamma, factor = (real)(gamma * lambda);
-#pragma omp parallel for schedule(static)
-    for (int64_t b0 = 0; b0 < B; b0 += 64) {
-        int64_t b1 = b0 + 64 < B ? b0 + 64 : B;
-        real g[64];
-        for (int64_t i = 0; i < 64; ++i) g[i] = (real)0;
-        for (int64_t t = T - 1; t >= 0; --t) {
-            const real* v0 = value + t * B;
+#pragma omp parallel
+    {
+        int64_t b0, b1;
+        col_range(B, omp_get_thread_num(), omp_get_num_threads(), &b0, &b1);
+        const int64_t w = b1 - b0;
+        real* g = (real*)calloc((size_t)(w > 0 ? w : 1), sizeof(real));
+        for (int64_t t = T - 1; t >= 0 && w > 0; --t) {
+            const real* v0 = value + t * B + b0;
             const real* v1 = v0 + B;
-            const real* r = reward + t * B;
-            real* a = adv + t * B;
+            const real* r = reward + t * B + b0;
+            real* a = adv + t * B + b0;
             const real dt = d[t];
-            for (int64_t b = b0; b < b1; ++b) {
+            for (int64_t b = 0; b < w; ++b) {
                 real delta = (r[b] + g_r * v1[b]) - v0[b];
-                real gi = dt * delta + factor * g[b - b0];
-                g[b - b0] = gi;
+                real gi = dt * delta + factor * g[b];
+                g[b] = gi;
                 a[b] = gi / dt;
             }
         }
+        free(g);
     }
     free(d);
 }
@@ -161,24 +185,29 @@ void FN(orc_gae_backward)(const real* grad_adv, real* grad_value, real* grad_rew
     real* d = (real*)malloc(sizeof(real) * (size_t)T);
     gae_denoms(T, lambda, d);
     const real g_r = (real)gamma, factor = (real)(gamma * lambda);
-#pragma omp parallel for schedule(static)
-    for (int64_t b0 = 0; b0 < B; b0 += 64) {
-        int64_t b1 = b0 + 64 < B ? b0 + 64 : B;
-        real gh[64], prev[64];
-        for (int64_t i = 0; i < 64; ++i) gh[i] = prev[i] = (real)0;
-        for (int64_t t = 0; t < T; ++t) {
-            const real* G = grad_adv + t * B;
+#pragma omp parallel
+    {
+        int64_t b0, b1;
+        col_range(B, omp_get_thread_num(), omp_get_num_threads(), &b0, &b1);
+        const int64_t w = b1 - b0;
+        real* gh = (real*)calloc((size_t)(w > 0 ? w : 1) * 2, sizeof(real));
+        real* prev = gh + (w > 0 ? w : 1);
+        for (int64_t t = 0; t < T && w > 0; ++t) {
+            const real* G = grad_adv + t * B + b0;
+            real* gr = grad_reward + t * B + b0;
+            real* gv = grad_value + t * B + b0;
             const real dt = d[t];
-            for (int64_t b = b0; b < b1; ++b) {
-                real h = G[b] / dt + factor * gh[b - b0];
-                gh[b - b0] = h;
+            for (int64_t b = 0; b < w; ++b) {
+                real h = G[b] / dt + factor * gh[b];
+                gh[b] = h;
                 real dd = dt * h;
-                grad_reward[t * B + b] = dd;
-                grad_value[t * B + b] = g_r * prev[b - b0] - dd;
-                prev[b - b0] = dd;
+                gr[b] = dd;
+                gv[b] = g_r * prev[b] - dd;
+                prev[b] = dd;
             }
         }
-        for (int64_t b = b0; b < b1; ++b) grad_value[T * B + b] = g_r * prev[b - b0];
+        for (int64_t b = 0; b < w; ++b) grad_value[T * B + b0 + b] = g_r * prev[b];
+        free(gh);
     }
     free(d);
 }

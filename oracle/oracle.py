@@ -81,6 +81,16 @@ def set_threads(n: int) -> None:
         pass
 
 
+def place(arr):
+    """Copy `arr` (2-D) into a fresh array whose pages are first-touched by the OpenMP threads that
+    will later stream them (NUMA placement for the CPU-baseline timing only)."""
+    arr = np.ascontiguousarray(arr)
+    out = np.empty_like(arr)
+    rows, B = arr.shape
+    _call(arr.dtype, "orc_place_copy", out, arr, c_i64(rows), c_i64(B))
+    return out
+
+
 # ------------------------------------------------------------------------------------------- gae
 def gae_forward(value, reward, gamma=0.99, lambda_=0.97):
     dt = value.dtype
