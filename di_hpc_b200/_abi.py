@@ -30,7 +30,27 @@ SIGNATURES = {
     "hpc_rll_gae_forward_ld": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
     "hpc_rll_gae_backward_ld": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
     "hpc_rll_gae_fwd_bwd_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl]),
+    "hpc_rll_td_lambda_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_i64, c_vp,
+                                          c_sz, c_vp]),
+    "hpc_rll_td_lambda_backward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "hpc_rll_vtrace_forward": (c_int, [c_vp] * 9 + [c_i64] * 3 + [c_dbl] * 5 + [c_i64, c_vp, c_sz, c_vp]),
+    "hpc_rll_vtrace_backward": (c_int, [c_vp] * 10 + [c_i64] * 4 + [c_vp]),
+    "hpc_rll_upgo_forward": (c_int, [c_vp] * 7 + [c_i64] * 4 + [c_vp, c_sz, c_vp]),
+    "hpc_rll_upgo_backward": (c_int, [c_vp] * 5 + [c_i64] * 3 + [c_vp]),
+    "hpc_rll_ppo_forward": (c_int, [c_vp] * 11 + [c_i64, c_i64, c_dbl, c_int, c_dbl, c_i64, c_vp, c_sz, c_vp]),
+    "hpc_rll_ppo_backward": (c_int, [c_vp] * 10 + [c_i64] * 3 + [c_vp]),
+    "hpc_rll_q_nstep_td_forward": (c_int, [c_vp] * 10 + [c_i64] * 3 + [c_dbl, c_int, c_i64, c_vp, c_sz, c_vp]),
+    "hpc_rll_q_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 2 + [c_vp]),
+    "hpc_rll_dist_nstep_td_forward": (c_int, [c_vp] * 10 + [c_i64] * 4 + [c_dbl] * 3 + [c_i64, c_vp, c_sz, c_vp]),
+    "hpc_rll_dist_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 3 + [c_vp]),
+    "hpc_rll_qrdqn_nstep_td_forward": (c_int, [c_vp] * 11 + [c_i64] * 4 + [c_dbl, c_i64, c_vp, c_sz, c_vp]),
+    "hpc_rll_qrdqn_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 3 + [c_vp]),
+    "hpc_rll_iqn_nstep_td_forward": (c_int, [c_vp] * 12 + [c_i64] * 5 + [c_dbl, c_dbl, c_i64, c_vp, c_sz, c_vp]),
+    "hpc_rll_iqn_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 3 + [c_vp]),
 }
+
+OP_GAE, OP_TD_LAMBDA, OP_VTRACE, OP_UPGO, OP_PPO, OP_Q_NSTEP_TD, OP_DIST_NSTEP_TD, OP_QRDQN_NSTEP_TD, \
+    OP_IQN_NSTEP_TD = range(9)
 
 _lib = None
 
@@ -86,6 +106,19 @@ def require_i64_cuda(name: str, t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.int64:
         raise TypeError("%s must be int64, got %s" % (name, t.dtype))
     return t.contiguous()
+
+
+def workspace(op: int, T: int, B: int, N: int, device) -> torch.Tensor:
+    """Allocate the scratch buffer an op asks for (torch caching allocator; stream-ordered reuse)."""
+    n = int(lib().hpc_rll_workspace_bytes(op, T, B, N))
+    return torch.empty(max(n, 8), dtype=torch.uint8, device=device)
+
+
+def grad_scalar(g: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """Upstream gradient of a scalar loss as a 1-element fp32 device tensor (never read on the host)."""
+    if g is None:
+        return torch.zeros(1, dtype=torch.float32, device=like.device)
+    return g.reshape(1).to(dtype=torch.float32, device=like.device).contiguous()
 
 
 def launch_count() -> int:

@@ -1,0 +1,51 @@
+// elementwise.cu -- host launcher of the shared scale/copy kernel (see reduce.cuh).
+#include "reduce.cuh"
+
+namespace hpcrll {
+
+// out[i] = scale[0] * in[i] (i < n);  out[i] = 0 (n <= i < n + zero_tail).  float4-vectorised when
+// both pointers are 16B aligned.  Used by the backward of every op whose forward already produced
+// d(loss)/d(input) up to the upstream gradient (the reference does the same with grad_buf,
+// td_lambda_kernel.h:42-51, vtrace_kernel.h:225-233, q_nstep_td_kernel.h:53-62).
+__global__ void __launch_bounds__(256) scale_copy_kernel(const float* __restrict__ in,
+                                                          const float* __restrict__ scale, float* __restrict__ out,
+                                                          int64_t n, int64_t zero_tail, int vec4) {
+    const float s = __ldg(scale);
+    const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    if (vec4) {
+        const int64_t n4 = n >> 2;
+        const float4* in4 = reinterpret_cast<const float4*>(in);
+        float4* out4 = reinterpret_cast<float4*>(out);
+        for (int64_t i = tid; i < n4; i += nth) {
+            float4 x = ld_stream4(in4 + i);
+            x.x *= s;
+            x.y *= s;
+            x.z *= s;
+            x.w *= s;
+            st_stream4(out4 + i, x);
+        }
+        for (int64_t i = (n4 << 2) + tid; i < n; i += nth) out[i] = s * in[i];
+    } else {
+        for (int64_t i = tid; i < n; i += nth) out[i] = s * in[i];
+    }
+    for (int64_t i = n + tid; i < n + zero_tail; i += nth) out[i] = 0.f;
+}
+
+
+int launch_scale_copy(const float* in, const float* scale_dev, float* out, int64_t n, int64_t zero_tail,
+                      cudaStream_t stream) {
+    if (n + zero_tail <= 0) return HPC_RLL_OK;
+    const int vec4 = aligned16(in) && aligned16(out) ? 1 : 0;
+    const int64_t work = vec4 ? (n + 3) / 4 : n;
+    int64_t blocks = (work + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    scale_copy_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(in, scale_dev, out, n, zero_tail, vec4);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+}  // namespace hpcrll

@@ -1,0 +1,267 @@
+// ppo.cu -- PPO clipped-surrogate losses, forward and backward, for sm_100a.
+//
+// Semantics: hpc_rll/origin/ppo.py:51-80 (ppo_error): policy loss with clip and optional dual clip,
+// clipped value loss, entropy, approx_kl, clipfrac.  No T axis, no recurrence: one streaming pass.
+// Tie rules follow autograd (torch.min/max split the gradient on exact ties, clamp passes it on the
+// closed interval) -- SURVEY.md A.5, restated in oracle/oracle.c orc_ppo.
+// Replaces PPOForward/PPOBackward (src/rl_utils/ppo.cu:8-111) and the 5 kernels of
+// include/hpc/rll/cuda/rl_utils/ppo_kernel.h:12-283 (block-per-row softmax x2, 5 atomics, three
+// (B,N) gradient buffers written by the forward, two host syncs for the info scalars).
+//
+// Forward = ONE kernel: both logits rows of a sample live in the registers of a sub-warp group;
+// lane 0 of the group evaluates the scalar loss terms, stores the two per-sample coefficients the
+// backward needs (pol_coef = dpolicy/dlogp_new[a], val_coef = dvalue_loss/dvalue_new) and feeds the
+// 5 fixed-order reductions.  Backward = shared softmax-gradient row kernel + scale of val_coef.
+#include "softmax_rows.cuh"
+
+namespace hpcrll {
+
+struct PpoParams {
+    float lo, hi, eps, dual;  // 1-clip, 1+clip, clip, dual_clip (<=0: off)
+    int use_value_clip;
+    float inv_n;
+};
+
+// scalar part for one sample; returns the five loss terms' contributions and the two coefficients
+__device__ __forceinline__ void ppo_sample(const PpoParams& P, float lpn, float lpo, float H, float ad, float vn,
+                                           float vo, float rt, float w, double (&acc)[5], float& pol_coef,
+                                           float& val_coef) {
+    const float ratio = expf(lpn - lpo);
+    const float s1 = ratio * ad;
+    const float rcl = fminf(fmaxf(ratio, P.lo), P.hi);
+    const float s2 = rcl * ad;
+    const float m = fminf(s1, s2);
+    const float in_range = (ratio >= P.lo && ratio <= P.hi) ? 1.f : 0.f;
+    const float g1 = s1 < s2 ? 1.f : (s1 == s2 ? 0.5f : 0.f);
+    float dm = g1 * ad + (1.f - g1) * ad * in_range;
+    float pol = m;
+    if (P.dual > 0.f) {
+        const float d = P.dual * ad;
+        const float gm = m > d ? 1.f : (m == d ? 0.5f : 0.f);
+        pol = fmaxf(m, d);
+        dm *= gm;
+    }
+    const float e1 = rt - vn;
+    const float v1 = e1 * e1;
+    float vl, dval;
+    if (P.use_value_clip) {
+        const float dvv = vn - vo;
+        const float cl = fminf(fmaxf(dvv, -P.eps), P.eps);
+        const float e2 = rt - (vo + cl);
+        const float v2 = e2 * e2;
+        const float inr = (dvv >= -P.eps && dvv <= P.eps) ? 1.f : 0.f;
+        const float k1 = v1 > v2 ? 1.f : (v1 == v2 ? 0.5f : 0.f);
+        vl = fmaxf(v1, v2);
+        dval = k1 * (-2.f * e1) + (1.f - k1) * (-2.f * e2) * inr;
+    } else {
+        vl = v1;
+        dval = -2.f * e1;
+    }
+    acc[0] += static_cast<double>(-pol * w);
+    acc[1] += static_cast<double>(vl * w);
+    acc[2] += static_cast<double>(H * w);
+    acc[3] += static_cast<double>(lpo - lpn);
+    acc[4] += (ratio > P.hi || ratio < P.lo) ? 1.0 : 0.0;
+    pol_coef = -(dm * ratio) * w * P.inv_n;
+    val_coef = 0.5f * dval * w * P.inv_n;
+}
+
+template <int KMAX, bool VEC>
+__global__ void __launch_bounds__(256) ppo_rows_fwd(const float* __restrict__ logits_new,
+                                                     const float* __restrict__ logits_old,
+                                                     const int64_t* __restrict__ action,
+                                                     const float* __restrict__ value_new,
+                                                     const float* __restrict__ value_old,
+                                                     const float* __restrict__ adv, const float* __restrict__ ret,
+                                                     const float* __restrict__ weight, float* __restrict__ pol_coef,
+                                                     float* __restrict__ val_coef, double* __restrict__ partials,
+                                                     const PpoParams P, int64_t R, int N, int G, int log2G) {
+    using Row = RowRegs<KMAX, VEC>;
+    constexpr int W = Row::W;
+    __shared__ double red[5 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lig = lane & (G - 1), gw = lane >> log2G;
+    const int rows_per_warp = 32 >> log2G;
+    const int rows_per_block = rows_per_warp * 8;
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
+        const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
+        const bool active = row < R;
+        Row rn, ro;
+        rn.load(logits_new + row * N, N, G, lig, active);
+        ro.load(logits_old + row * N, N, G, lig, active);
+        const int a = active ? static_cast<int>(action[row]) : -1;
+        float mn, sn, mo, so;
+        rn.max_sumexp(G, mn, sn);
+        ro.max_sumexp(G, mo, so);
+        const float lsn = logf(sn), lso = logf(so);
+        float hpart = 0.f, seln = 0.f, selo = 0.f;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const int i = j * W + q;
+                const int idx = rn.index(j, q, G, lig);
+                if (idx < N) {
+                    const float lp = row_logp<true>(rn.x[i], mn, lsn);
+                    hpart += expf(lp) * lp;
+                    if (idx == a) {
+                        seln = lp;
+                        selo = row_logp<true>(ro.x[i], mo, lso);
+                    }
+                }
+            }
+        }
+        const float H = -group_sum(hpart, G);
+        seln = group_sum(seln, G);
+        selo = group_sum(selo, G);
+        if (active && lig == 0) {
+            float pc, vc;
+            ppo_sample(P, seln, selo, H, adv[row], value_new[row], value_old[row], ret[row],
+                       weight ? weight[row] : 1.f, acc, pc, vc);
+            pol_coef[row] = pc;
+            val_coef[row] = vc;
+        }
+    }
+    block_sum<5>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) partials[static_cast<size_t>(k) * gridDim.x + blockIdx.x] = acc[k];
+    }
+}
+
+__global__ void __launch_bounds__(256) ppo_rows_fwd_loop(const float* __restrict__ logits_new,
+                                                          const float* __restrict__ logits_old,
+                                                          const int64_t* __restrict__ action,
+                                                          const float* __restrict__ value_new,
+                                                          const float* __restrict__ value_old,
+                                                          const float* __restrict__ adv, const float* __restrict__ ret,
+                                                          const float* __restrict__ weight,
+                                                          float* __restrict__ pol_coef, float* __restrict__ val_coef,
+                                                          double* __restrict__ partials, const PpoParams P, int64_t R,
+                                                          int N) {
+    __shared__ double red[5 * 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < R; row += static_cast<int64_t>(gridDim.x) * 8) {
+        const float* xn = logits_new + row * N;
+        const float* xo = logits_old + row * N;
+        float mn = -INFINITY, mo = -INFINITY;
+        for (int k = lane; k < N; k += 32) {
+            mn = fmaxf(mn, xn[k]);
+            mo = fmaxf(mo, xo[k]);
+        }
+        mn = warp_max(mn);
+        mo = warp_max(mo);
+        float sn = 0.f, so = 0.f;
+        for (int k = lane; k < N; k += 32) {
+            sn += expf(xn[k] - mn);
+            so += expf(xo[k] - mo);
+        }
+        sn = warp_sum(sn);
+        so = warp_sum(so);
+        const float lsn = logf(sn), lso = logf(so);
+        float h = 0.f;
+        for (int k = lane; k < N; k += 32) {
+            const float lp = row_logp<true>(xn[k], mn, lsn);
+            h += expf(lp) * lp;
+        }
+        const float H = -warp_sum(h);
+        if (lane == 0) {
+            const int a = static_cast<int>(action[row]);
+            float pc, vc;
+            ppo_sample(P, row_logp<true>(xn[a], mn, lsn), row_logp<true>(xo[a], mo, lso), H, adv[row], value_new[row],
+                       value_old[row], ret[row], weight ? weight[row] : 1.f, acc, pc, vc);
+            pol_coef[row] = pc;
+            val_coef[row] = vc;
+        }
+    }
+    block_sum<5>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) partials[static_cast<size_t>(k) * gridDim.x + blockIdx.x] = acc[k];
+    }
+}
+
+size_t ppo_workspace_bytes() { return static_cast<size_t>(sm_count()) * 16 * 5 * 8 + 256; }
+
+}  // namespace hpcrll
+
+extern "C" {
+
+int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const int64_t* action,
+                        const float* value_new, const float* value_old, const float* adv, const float* return_,
+                        const float* weight, float* out5, float* pol_coef, float* val_coef, int64_t B, int64_t N,
+                        double clip_ratio, int use_value_clip, double dual_clip, int64_t global_B, void* workspace,
+                        size_t workspace_bytes, void* stream_) {
+    using namespace hpcrll;
+    cudaStream_t stream = as_stream(stream_);
+    HPC_REQUIRE(B > 0 && N > 0, "ppo_forward: sizes must be positive (B=%lld N=%lld)", (long long)B, (long long)N);
+    HPC_REQUIRE(logits_new && logits_old && action && value_new && value_old && adv && return_ && out5 && pol_coef &&
+                    val_coef && workspace,
+                "ppo_forward: null pointer");
+    HPC_REQUIRE(workspace_bytes >= ppo_workspace_bytes(), "ppo_forward: workspace too small");
+    HPC_REQUIRE(N < (int64_t(1) << 30), "ppo_forward: N too large");
+    HPC_REQUIRE(dual_clip <= 0.0 || dual_clip > 1.0, "ppo_forward: dual_clip must be > 1.0 (or <= 0 for None)");
+    if (global_B <= 0) global_B = B;
+    const double inv_n = 1.0 / static_cast<double>(global_B);
+    PpoParams P;
+    P.lo = static_cast<float>(1.0 - clip_ratio);
+    P.hi = static_cast<float>(1.0 + clip_ratio);
+    P.eps = static_cast<float>(clip_ratio);
+    P.dual = dual_clip > 0.0 ? static_cast<float>(dual_clip) : 0.f;
+    P.use_value_clip = use_value_clip;
+    P.inv_n = static_cast<float>(inv_n);
+    double* partials = static_cast<double*>(workspace);
+    const RowGeom ge = row_geom(N, aligned16(logits_new) && aligned16(logits_old));
+    int log2G = 0;
+    while ((1 << log2G) < ge.G) ++log2G;
+    const unsigned grid = rows_grid(B, ge.kmax == 0 ? 8 : (32 / ge.G) * 8);
+    const int n = static_cast<int>(N);
+#define HPC_PPO_ROWS(K, V)                                                                                       \
+    ppo_rows_fwd<K, V><<<grid, 256, 0, stream>>>(logits_new, logits_old, action, value_new, value_old, adv, return_, \
+                                                 weight, pol_coef, val_coef, partials, P, B, n, ge.G, log2G)
+    if (ge.kmax == 0)
+        ppo_rows_fwd_loop<<<grid, 256, 0, stream>>>(logits_new, logits_old, action, value_new, value_old, adv, return_,
+                                                    weight, pol_coef, val_coef, partials, P, B, n);
+    else if (ge.vec) {
+        if (ge.kmax == 1) HPC_PPO_ROWS(1, true);
+        else if (ge.kmax == 2) HPC_PPO_ROWS(2, true);
+        else HPC_PPO_ROWS(8, true);
+    } else {
+        if (ge.kmax == 1) HPC_PPO_ROWS(1, false);
+        else if (ge.kmax == 2) HPC_PPO_ROWS(2, false);
+        else HPC_PPO_ROWS(8, false);
+    }
+#undef HPC_PPO_ROWS
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    FinSpec spec;
+    const double sc[5] = {inv_n, 0.5 * inv_n, inv_n, inv_n, inv_n};
+    for (int k = 0; k < 5; ++k) {
+        spec.off[k] = k * static_cast<int>(grid);
+        spec.cnt[k] = static_cast<int>(grid);
+        spec.scale[k] = sc[k];
+    }
+    return launch_finalize_terms(partials, spec, 5, out5, stream);
+}
+
+int hpc_rll_ppo_backward(const float* grad_policy_loss, const float* grad_value_loss, const float* grad_entropy_loss,
+                         const float* logits_new, const int64_t* action, const float* weight, const float* pol_coef,
+                         const float* val_coef, float* grad_logits_new, float* grad_value_new, int64_t B, int64_t N,
+                         int64_t global_B, void* stream_) {
+    using namespace hpcrll;
+    cudaStream_t stream = as_stream(stream_);
+    HPC_REQUIRE(B > 0 && N > 0, "ppo_backward: sizes must be positive");
+    HPC_REQUIRE(grad_policy_loss && grad_value_loss && grad_entropy_loss && logits_new && action && pol_coef &&
+                    val_coef && grad_logits_new && grad_value_new,
+                "ppo_backward: null pointer");
+    if (global_B <= 0) global_B = B;
+    const double inv_n = 1.0 / static_cast<double>(global_B);
+    int rc = launch_softmax_grad_rows(logits_new, action, pol_coef, weight, grad_policy_loss, grad_entropy_loss, inv_n,
+                                      grad_logits_new, B, N, true, stream);
+    if (rc) return rc;
+    return launch_scale_copy(val_coef, grad_value_loss, grad_value_new, B, 0, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// softmax_rows.cu -- the softmax-gradient row kernel shared by V-trace, UPGO and PPO backward, and
+// the fixed-order loss finaliser.  See softmax_rows.cuh for the design.
+//
+// Replaces vtraceBackwardTargetOutput (include/hpc/rll/cuda/rl_utils/vtrace_kernel.h:235-273),
+// upgoBackwardKernel (upgo_kernel.h:96-108) and ppoBackwardLogitsNew (ppo_kernel.h:252-283), which
+// re-read (T,B,N) buffers saved by the forward; here the softmax is recomputed from the logits.
+#include "softmax_rows.cuh"
+
+namespace hpcrll {
+
+template <int KMAX, bool VEC, bool ENT, bool CAT>
+__global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __restrict__ logits,
+                                                                 const int64_t* __restrict__ action,
+                                                                 const float* __restrict__ c1,
+                                                                 const float* __restrict__ w,
+                                                                 const float* __restrict__ g1,
+                                                                 const float* __restrict__ g2, float inv_n,
+                                                                 float* __restrict__ grad, int64_t R, int N, int G,
+                                                                 int log2G) {
+    using Row = RowRegs<KMAX, VEC>;
+    constexpr int W = Row::W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lig = lane & (G - 1), gw = lane >> log2G;
+    const int rows_per_warp = 32 >> log2G;
+    const int rows_per_block = rows_per_warp * 8;
+    const float s1 = __ldg(g1);
+    const float s2 = ENT ? __ldg(g2) * inv_n : 0.f;
+    for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
+        const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
+        const bool active = row < R;
+        Row rr;
+        rr.load(logits + row * N, N, G, lig, active);
+        float m, s;
+        rr.max_sumexp(G, m, s);
+        const float logs = logf(s);
+        const int a = active ? static_cast<int>(action[row]) : -1;
+        const float c = active ? s1 * c1[row] : 0.f;
+        const float e2 = ENT ? s2 * ((w && active) ? w[row] : 1.f) : 0.f;
+        float lp[Row::NE], p[Row::NE];
+        float hpart = 0.f;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const int i = j * W + q;
+                const bool ok = rr.index(j, q, G, lig) < N;
+                lp[i] = row_logp<CAT>(rr.x[i], m, logs);
+                p[i] = ok ? expf(lp[i]) : 0.f;
+                if (ENT && ok) hpart += p[i] * lp[i];
+            }
+        }
+        const float H = ENT ? -group_sum(hpart, G) : 0.f;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+            float o[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) {
+                const int i = j * W + q;
+                const int idx = rr.index(j, q, G, lig);
+                float gq = c * ((idx == a ? 1.f : 0.f) - p[i]);
+                if (ENT) gq += e2 * (-p[i] * (lp[i] + H));
+                o[q] = gq;
+            }
+            const int e0 = rr.index(j, 0, G, lig);
+            if (active && e0 < N) {
+                if (VEC)
+                    st_stream4(reinterpret_cast<float4*>(grad + row * N + e0),
+                               make_float4(o[0], o[W > 1 ? 1 : 0], o[W > 2 ? 2 : 0], o[W > 3 ? 3 : 0]));
+                else
+                    st_stream(grad + row * N + e0, o[0]);
+            }
+        }
+    }
+}
+
+// N too large for the register-resident path: one warp per row, strided passes over the row.
+template <bool ENT, bool CAT>
+__global__ void __launch_bounds__(256) softmax_grad_rows_loop_kernel(const float* __restrict__ logits,
+                                                                      const int64_t* __restrict__ action,
+                                                                      const float* __restrict__ c1,
+                                                                      const float* __restrict__ w,
+                                                                      const float* __restrict__ g1,
+                                                                      const float* __restrict__ g2, float inv_n,
+                                                                      float* __restrict__ grad, int64_t R, int N) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float s1 = __ldg(g1);
+    const float s2 = ENT ? __ldg(g2) * inv_n : 0.f;
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < R; row += static_cast<int64_t>(gridDim.x) * 8) {
+        const float* x = logits + row * N;
+        float m = -INFINITY;
+        for (int k = lane; k < N; k += 32) m = fmaxf(m, x[k]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int k = lane; k < N; k += 32) s += expf(x[k] - m);
+        s = warp_sum(s);
+        const float logs = logf(s);
+        float H = 0.f;
+        if (ENT) {
+            float h = 0.f;
+            for (int k = lane; k < N; k += 32) {
+                const float l = row_logp<CAT>(x[k], m, logs);
+                h += expf(l) * l;
+            }
+            H = -warp_sum(h);
+        }
+        const int a = static_cast<int>(action[row]);
+        const float c = s1 * c1[row];
+        const float e2 = ENT ? s2 * (w ? w[row] : 1.f) : 0.f;
+        for (int k = lane; k < N; k += 32) {
+            const float l = row_logp<CAT>(x[k], m, logs);
+            const float p = expf(l);
+            float gq = c * ((k == a ? 1.f : 0.f) - p);
+            if (ENT) gq += e2 * (-p * (l + H));
+            grad[row * N + k] = gq;
+        }
+    }
+}
+
+template <bool ENT, bool CAT>
+static int launch_grad_t(const float* logits, const int64_t* action, const float* c1, const float* w,
+                         const float* g1, const float* g2, float inv_n, float* grad, int64_t R, int N,
+                         cudaStream_t stream) {
+    const RowGeom ge = row_geom(N, aligned16(logits) && aligned16(grad));
+    int log2G = 0;
+    while ((1 << log2G) < ge.G) ++log2G;
+    const int rows_per_block = (32 / ge.G) * 8;
+    const unsigned grid = rows_grid(R, ge.kmax == 0 ? 8 : rows_per_block);
+#define HPC_GRAD_LAUNCH(K, V)                                                                                    \
+    softmax_grad_rows_kernel<K, V, ENT, CAT><<<grid, 256, 0, stream>>>(logits, action, c1, w, g1, g2, inv_n, grad, \
+                                                                       R, N, ge.G, log2G)
+    if (ge.kmax == 0)
+        softmax_grad_rows_loop_kernel<ENT, CAT><<<grid, 256, 0, stream>>>(logits, action, c1, w, g1, g2, inv_n, grad,
+                                                                         R, N);
+    else if (ge.vec) {
+        if (ge.kmax == 1) HPC_GRAD_LAUNCH(1, true);
+        else if (ge.kmax == 2) HPC_GRAD_LAUNCH(2, true);
+        else HPC_GRAD_LAUNCH(8, true);
+    } else {
+        if (ge.kmax == 1) HPC_GRAD_LAUNCH(1, false);
+        else if (ge.kmax == 2) HPC_GRAD_LAUNCH(2, false);
+        else HPC_GRAD_LAUNCH(8, false);
+    }
+#undef HPC_GRAD_LAUNCH
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+int launch_softmax_grad_rows(const float* logits, const int64_t* action, const float* c1, const float* w,
+                             const float* g1, const float* g2, double inv_n, float* grad, int64_t R, int64_t N,
+                             bool categorical, cudaStream_t stream) {
+    if (R <= 0 || N <= 0) return HPC_RLL_OK;
+    HPC_REQUIRE(N < (int64_t(1) << 30), "softmax rows: N too large");
+    const float in = static_cast<float>(inv_n);
+    if (g2 != nullptr) {
+        return launch_grad_t<true, true>(logits, action, c1, w, g1, g2, in, grad, R, static_cast<int>(N), stream);
+    }
+    if (categorical)
+        return set_error(HPC_RLL_ENOSUP, "softmax rows: categorical form without entropy term is not instantiated");
+    return launch_grad_t<false, false>(logits, action, c1, w, g1, g2, in, grad, R, static_cast<int>(N), stream);
+}
+
+// ---- fixed-order finaliser for several loss terms with different partial counts ---------------------
+__global__ void __launch_bounds__(256) finalize_terms_kernel(const double* __restrict__ partials,
+                                                              const __grid_constant__ FinSpec spec, int nterms,
+                                                              float* __restrict__ out) {
+    __shared__ double scratch[32];
+    for (int k = 0; k < nterms; ++k) {
+        double a = 0.0;
+        for (int i = threadIdx.x; i < spec.cnt[k]; i += 256) a += partials[spec.off[k] + i];
+        double v[1] = {a};
+        block_sum<1>(v, scratch);
+        if (threadIdx.x == 0) out[k] = static_cast<float>(v[0] * spec.scale[k]);
+    }
+}
+
+int launch_finalize_terms(const double* partials, const FinSpec& spec, int nterms, float* out,
+                          cudaStream_t stream) {
+    finalize_terms_kernel<<<1, 256, 0, stream>>>(partials, spec, nterms, out);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+}  // namespace hpcrll

@@ -83,6 +83,121 @@ int hpc_rll_gae_fwd_bwd_host(const float* h_value, const float* h_reward, const 
                              float* h_grad_value, float* h_grad_reward, int64_t T, int64_t B, double gamma,
                              double lambda);
 
+/* ---- TD(lambda) ----------------------------------------------------------------------------
+ * replaces TdLambdaForward / TdLambdaBackward (/root/reference/src/rl_utils/td_lambda.cu:8-52, kernels
+ * include/hpc/rll/cuda/rl_utils/td_lambda_kernel.h:11-51); semantics of hpc_rll/origin/td.py:148-176.
+ *   forward : value (T+1,B), reward (T,B), weight (T,B) or NULL (= ones)
+ *             -> loss[1] = 0.5*mean(w*(ret-v)^2),  grad_buf (T,B) = dloss/dvalue[:T] (no upstream grad)
+ *   backward: grad_loss[1] (device), grad_buf -> grad_value (T+1,B) (row T is zero) */
+int hpc_rll_td_lambda_forward(const float* value, const float* reward, const float* weight, float* loss,
+                              float* grad_buf, int64_t T, int64_t B, double gamma, double lambda,
+                              int64_t global_B, void* workspace, size_t workspace_bytes, void* stream);
+int hpc_rll_td_lambda_backward(const float* grad_loss, const float* grad_buf, float* grad_value, int64_t T,
+                               int64_t B, void* stream);
+
+/* ---- V-trace --------------------------------------------------------------------------------
+ * replaces VTraceForward / VTraceBackward (/root/reference/src/rl_utils/vtrace.cu:8-130, kernels
+ * include/hpc/rll/cuda/rl_utils/vtrace_kernel.h:11-273); semantics of hpc_rll/origin/vtrace.py:63-79.
+ *   forward : target_output, behaviour_output (T,B,N); action (T,B) int64; value (T+1,B); reward (T,B);
+ *             weight (T,B) or NULL -> losses[3] = {policy, value, entropy};
+ *             saved for backward: pg_coef (T,B) = -adv*w/n, gv_buf (T,B) = 2(v-ret)w/n   (n = T*global_B)
+ *   backward: three upstream gradients (device scalars) -> grad_target_output (T,B,N), grad_value (T+1,B) */
+int hpc_rll_vtrace_forward(const float* target_output, const float* behaviour_output, const int64_t* action,
+                           const float* value, const float* reward, const float* weight, float* losses,
+                           float* pg_coef, float* gv_buf, int64_t T, int64_t B, int64_t N, double gamma,
+                           double lambda, double rho_clip_ratio, double c_clip_ratio, double rho_pg_clip_ratio,
+                           int64_t global_B, void* workspace, size_t workspace_bytes, void* stream);
+int hpc_rll_vtrace_backward(const float* grad_policy_loss, const float* grad_value_loss,
+                            const float* grad_entropy_loss, const float* target_output, const int64_t* action,
+                            const float* weight, const float* pg_coef, const float* gv_buf, float* grad_target_output,
+                            float* grad_value, int64_t T, int64_t B, int64_t N, int64_t global_B, void* stream);
+
+/* ---- UPGO -----------------------------------------------------------------------------------
+ * replaces UpgoForward / UpgoBackward (/root/reference/src/rl_utils/upgo.cu:8-69, kernels
+ * include/hpc/rll/cuda/rl_utils/upgo_kernel.h:11-108); semantics of hpc_rll/origin/upgo.py:40-70.
+ *   forward : target_output (T,B,N); rhos (T,B); action (T,B) int64; rewards (T,B); bootstrap_values (T+1,B)
+ *             -> loss[1]; saved for backward: coef (T,B) = -adv/n
+ *   backward: grad_loss (device scalar) -> grad_target_output (T,B,N) */
+int hpc_rll_upgo_forward(const float* target_output, const float* rhos, const int64_t* action,
+                         const float* rewards, const float* bootstrap_values, float* loss, float* coef, int64_t T,
+                         int64_t B, int64_t N, int64_t global_B, void* workspace, size_t workspace_bytes,
+                         void* stream);
+int hpc_rll_upgo_backward(const float* grad_loss, const float* target_output, const int64_t* action,
+                          const float* coef, float* grad_target_output, int64_t T, int64_t B, int64_t N,
+                          void* stream);
+
+/* ---- PPO ------------------------------------------------------------------------------------
+ * replaces PPOForward / PPOBackward (/root/reference/src/rl_utils/ppo.cu:8-111, kernels
+ * include/hpc/rll/cuda/rl_utils/ppo_kernel.h:12-283); semantics of hpc_rll/origin/ppo.py:51-80.
+ *   forward : logits_new, logits_old (B,N); action (B) int64; value_new, value_old, adv, return_ (B);
+ *             weight (B) or NULL; dual_clip <= 0 means None
+ *             -> out5 = {policy_loss, value_loss, entropy_loss, approx_kl, clipfrac};
+ *             saved: pol_coef (B) = dpolicy_loss/dlogp_new[a], val_coef (B) = dvalue_loss/dvalue_new
+ *   backward: three upstream gradients (device scalars) -> grad_logits_new (B,N), grad_value_new (B) */
+int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const int64_t* action,
+                        const float* value_new, const float* value_old, const float* adv, const float* return_,
+                        const float* weight, float* out5, float* pol_coef, float* val_coef, int64_t B, int64_t N,
+                        double clip_ratio, int use_value_clip, double dual_clip, int64_t global_B, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int hpc_rll_ppo_backward(const float* grad_policy_loss, const float* grad_value_loss, const float* grad_entropy_loss,
+                         const float* logits_new, const int64_t* action, const float* weight, const float* pol_coef,
+                         const float* val_coef, float* grad_logits_new, float* grad_value_new, int64_t B, int64_t N,
+                         int64_t global_B, void* stream);
+
+/* ---- n-step TD-error family ------------------------------------------------------------------
+ * Common: reward (T,B) with T = nstep; done (B) as FLOAT 0/1 (the reference reads it as float*,
+ * src/rl_utils/q_nstep_td.cu:39); weight (B) or NULL; action / next_n_action (B) int64.
+ * Each forward returns loss[1], td_err (B) and grad_buf = d loss / d(gathered row) (no upstream grad);
+ * each backward scatters g*grad_buf into the action's slot of a dense, otherwise zero gradient. */
+
+/* q_nstep_td_error / q_nstep_td_error_with_rescale: replaces QNStepTd{,Rescale}{Forward,Backward}
+ * (/root/reference/src/rl_utils/q_nstep_td.cu, q_nstep_td_rescale.cu; kernels q_nstep_td_kernel.h:11-62,
+ * q_nstep_td_rescale_kernel.h:11-72); semantics hpc_rll/origin/td.py:252-291, 294-340.
+ *   q, next_n_q (B,N); grad_buf (B); grad_q (B,N) */
+int hpc_rll_q_nstep_td_forward(const float* q, const float* next_n_q, const int64_t* action,
+                               const int64_t* next_n_action, const float* reward, const float* done,
+                               const float* weight, float* loss, float* td_err, float* grad_buf, int64_t T,
+                               int64_t B, int64_t N, double gamma, int rescale, int64_t global_B, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int hpc_rll_q_nstep_td_backward(const float* grad_loss, const float* grad_buf, const int64_t* action,
+                                float* grad_q, int64_t B, int64_t N, void* stream);
+
+/* dist_nstep_td_error (C51): replaces DistNStepTd{Forward,Backward} (/root/reference/src/rl_utils/
+ * dist_nstep_td.cu:8-98, kernels dist_nstep_td_kernel.h:11-107); semantics hpc_rll/origin/td.py:29-143.
+ *   dist, next_n_dist (B,N,n_atom); grad_buf (B,n_atom); grad_dist (B,N,n_atom) */
+int hpc_rll_dist_nstep_td_forward(const float* dist, const float* next_n_dist, const int64_t* action,
+                                  const int64_t* next_n_action, const float* reward, const float* done,
+                                  const float* weight, float* loss, float* td_err, float* grad_buf, int64_t T,
+                                  int64_t B, int64_t N, int64_t n_atom, double gamma, double v_min, double v_max,
+                                  int64_t global_B, void* workspace, size_t workspace_bytes, void* stream);
+int hpc_rll_dist_nstep_td_backward(const float* grad_loss, const float* grad_buf, const int64_t* action,
+                                   float* grad_dist, int64_t B, int64_t N, int64_t n_atom, void* stream);
+
+/* qrdqn_nstep_td_error: replaces QRDQNNStepTDError{Forward,Backward} (/root/reference/src/rl_utils/
+ * qrdqn_nstep_td_error.cu:8-95, kernels qrdqn_nstep_td_error_kernel.h:11-106); semantics
+ * hpc_rll/origin/td.py:455-517 with `tau` the INTEGER quantile count (as the reference wrapper passes it).
+ *   q, next_n_q (B,N,tau); value_gamma (B) or NULL (= gamma^T); grad_buf (B,tau); grad_q (B,N,tau) */
+int hpc_rll_qrdqn_nstep_td_forward(const float* q, const float* next_n_q, const int64_t* action,
+                                   const int64_t* next_n_action, const float* reward, const float* done,
+                                   const float* weight, const float* value_gamma, float* loss, float* td_err,
+                                   float* grad_buf, int64_t tau, int64_t T, int64_t B, int64_t N, double gamma,
+                                   int64_t global_B, void* workspace, size_t workspace_bytes, void* stream);
+int hpc_rll_qrdqn_nstep_td_backward(const float* grad_loss, const float* grad_buf, const int64_t* action,
+                                    float* grad_q, int64_t tau, int64_t B, int64_t N, void* stream);
+
+/* iqn_nstep_td_error: replaces IQNNStepTDError{Forward,Backward} (/root/reference/src/rl_utils/
+ * iqn_nstep_td_error.cu:8-100, kernels iqn_nstep_td_error_kernel.h:11-108); semantics
+ * hpc_rll/origin/td.py:361-448.
+ *   q (tau,B,N); next_n_q (tau',B,N); replay_quantiles (tau,B); grad_buf (tau,B); grad_q (tau,B,N) */
+int hpc_rll_iqn_nstep_td_forward(const float* q, const float* next_n_q, const int64_t* action,
+                                 const int64_t* next_n_action, const float* reward, const float* done,
+                                 const float* replay_quantiles, const float* weight, const float* value_gamma,
+                                 float* loss, float* td_err, float* grad_buf, int64_t tau, int64_t tau_prime,
+                                 int64_t T, int64_t B, int64_t N, double gamma, double kappa, int64_t global_B,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int hpc_rll_iqn_nstep_td_backward(const float* grad_loss, const float* grad_buf, const int64_t* action,
+                                  float* grad_q, int64_t tau, int64_t B, int64_t N, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

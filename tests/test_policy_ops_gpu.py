@@ -1,0 +1,202 @@
+"""V-trace, UPGO and PPO parity on the GPU (CUDA through the C ABI) vs the oracle and the
+origin-generated golden fixtures.  Tolerance: 1e-5 norm-relative (north_star) for every loss and
+gradient tensor; the gradient's exact-zero structure is checked where the op defines one."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as orc
+from tests._golden import Case, names, rel_err
+from tests._gpu import dev, host, need_cuda, rng
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def close(got, want, what):
+    e = rel_err(got, want)
+    assert e <= TOL, "%s: rel err %.3e" % (what, e)
+
+
+# ----------------------------------------------------------------------------------------- vtrace
+def run_vtrace(inp, hp, coef):
+    from hpc_rll.rl_utils.vtrace import VTrace
+    t = dev(inp["target_output"]).requires_grad_(True)
+    v = dev(inp["value"]).requires_grad_(True)
+    w = None if inp.get("weight") is None else dev(inp["weight"])
+    T, B, N = inp["target_output"].shape
+    l = VTrace(T, B, N)(t, dev(inp["behaviour_output"]), dev(inp["action"]), v, dev(inp["reward"]), w, **hp)
+    assert all(x.shape == (1, ) for x in l)
+    (coef[0] * l.policy_loss + coef[1] * l.value_loss + coef[2] * l.entropy_loss).sum().backward()
+    torch.cuda.synchronize()
+    return [float(x.item()) for x in l], host(t.grad), host(v.grad)
+
+
+def vtrace_inputs(g, T, B, N, use_w):
+    return dict(target_output=(g.standard_normal((T, B, N)) * 1.5).astype(np.float32),
+                behaviour_output=(g.standard_normal((T, B, N)) * 1.5).astype(np.float32),
+                action=g.integers(0, N, (T, B)).astype(np.int64),
+                value=g.standard_normal((T + 1, B), dtype=np.float32),
+                reward=g.standard_normal((T, B), dtype=np.float32),
+                weight=g.random((T, B), dtype=np.float32) if use_w else None)
+
+
+HP1 = dict(gamma=0.99, lambda_=0.95, rho_clip_ratio=1.0, c_clip_ratio=1.0, rho_pg_clip_ratio=1.0)
+HP2 = dict(gamma=0.9, lambda_=0.8, rho_clip_ratio=1.5, c_clip_ratio=0.9, rho_pg_clip_ratio=2.0)
+
+
+@pytest.mark.parametrize("T,B,N,use_w,hp", [(128, 128, 128, False, HP1), (16, 256, 16, True, HP2), (5, 7, 3, True, HP1),
+                                             (1, 2, 1, False, HP1), (33, 132, 6, True, HP2), (9, 260, 40, False, HP1),
+                                             (4, 64, 300, True, HP1), (12, 1024, 8, True, HP2), (6, 36, 1100, False, HP2),
+                                             (50, 4100, 4, False, HP1)])
+def test_vtrace_vs_oracle(T, B, N, use_w, hp):
+    need_cuda()
+    inp = vtrace_inputs(rng(T * 131 + B * 7 + N), T, B, N, use_w)
+    coef = [1.0, 0.5, -0.25]
+    losses, gt, gv = run_vtrace(inp, hp, coef)
+    o = orc.vtrace(inp["target_output"], inp["behaviour_output"], inp["action"], inp["value"], inp["reward"],
+                   inp["weight"], coef=coef, **hp)
+    for k, name in enumerate(("policy_loss", "value_loss", "entropy_loss")):
+        close(losses[k], o[name], name)
+    close(gt, o["grad_target_output"], "grad_target_output")
+    close(gv, o["grad_value"], "grad_value")
+    assert np.all(gv[-1] == 0)
+
+
+@pytest.mark.parametrize("name", names("vtrace"))
+def test_vtrace_vs_golden(name):
+    need_cuda()
+    c = Case(name)
+    inp = {k: c.inp(k) for k in ("target_output", "behaviour_output", "action", "value", "reward", "weight")}
+    hp = {k: c.attr(k) for k in HP1}
+    coef = [c.attr("coef_policy"), c.attr("coef_value"), c.attr("coef_entropy")]
+    losses, gt, gv = run_vtrace(inp, hp, coef)
+    for prec in (32, 64):
+        for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss")):
+            close(losses[k], c.out(nm, prec), nm)
+        close(gt, c.grad("target_output", prec), "grad_target_output")
+        close(gv, c.grad("value", prec), "grad_value")
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 99])
+def test_vtrace_scan_configs(cfg):
+    need_cuda()
+    from di_hpc_b200 import _abi
+    inp = vtrace_inputs(rng(cfg + 50), 21, 520, 8, True)
+    coef = [1.0, 1.0, 1.0]
+    try:
+        _abi.set_config(_abi.OP_VTRACE, cfg)
+        losses, gt, gv = run_vtrace(inp, HP2, coef)
+    finally:
+        _abi.set_config(_abi.OP_VTRACE, -1)
+    o = orc.vtrace(inp["target_output"], inp["behaviour_output"], inp["action"], inp["value"], inp["reward"],
+                   inp["weight"], coef=coef, **HP2)
+    close(losses[0], o["policy_loss"], "pg")
+    close(losses[1], o["value_loss"], "v")
+    close(gt, o["grad_target_output"], "gt")
+    close(gv, o["grad_value"], "gv")
+
+
+# ----------------------------------------------------------------------------------------- upgo
+def run_upgo(inp, coef):
+    from hpc_rll.rl_utils.upgo import UPGO
+    t = dev(inp["target_output"]).requires_grad_(True)
+    T, B, N = inp["target_output"].shape
+    loss = UPGO(T, B, N)(t, dev(inp["rhos"]), dev(inp["action"]), dev(inp["rewards"]), dev(inp["bootstrap_values"]))
+    assert loss.shape == (1, )
+    (coef * loss).sum().backward()
+    torch.cuda.synchronize()
+    return float(loss.item()), host(t.grad)
+
+
+@pytest.mark.parametrize("T,B,N", [(256, 256, 256), (16, 256, 16), (5, 7, 3), (1, 4, 3), (2, 4, 16), (33, 132, 6),
+                                   (20, 3, 33), (8, 1024, 8), (3, 40, 1100), (40, 4100, 4)])
+def test_upgo_vs_oracle(T, B, N):
+    need_cuda()
+    g = rng(T * 17 + B * 3 + N)
+    inp = dict(target_output=(g.standard_normal((T, B, N)) * 1.5).astype(np.float32),
+               rhos=(g.random((T, B)) * 2).astype(np.float32), action=g.integers(0, N, (T, B)).astype(np.int64),
+               rewards=g.standard_normal((T, B), dtype=np.float32),
+               bootstrap_values=g.standard_normal((T + 1, B), dtype=np.float32))
+    loss, gt = run_upgo(inp, -0.7)
+    o = orc.upgo(inp["target_output"], inp["rhos"], inp["action"], inp["rewards"], inp["bootstrap_values"], -0.7)
+    close(loss, o["loss"], "loss")
+    close(gt, o["grad_target_output"], "grad_target_output")
+
+
+@pytest.mark.parametrize("name", names("upgo"))
+def test_upgo_vs_golden(name):
+    need_cuda()
+    c = Case(name)
+    inp = {k: c.inp(k) for k in ("target_output", "rhos", "action", "rewards", "bootstrap_values")}
+    loss, gt = run_upgo(inp, c.attr("coef_loss"))
+    for prec in (32, 64):
+        close(loss, c.out("loss", prec), "loss")
+        close(gt, c.grad("target_output", prec), "grad_target_output")
+
+
+# ----------------------------------------------------------------------------------------- ppo
+def run_ppo(inp, clip_ratio, use_value_clip, dual_clip, coef):
+    from hpc_rll.rl_utils.ppo import PPO
+    ln = dev(inp["logits_new"]).requires_grad_(True)
+    vn = dev(inp["value_new"]).requires_grad_(True)
+    w = None if inp.get("weight") is None else dev(inp["weight"])
+    B, N = inp["logits_new"].shape
+    loss, info = PPO(B, N)(ln, dev(inp["logits_old"]), dev(inp["action"]), vn, dev(inp["value_old"]), dev(inp["adv"]),
+                           dev(inp["return_"]), w, clip_ratio, use_value_clip, dual_clip)
+    assert isinstance(info.approx_kl, float) and isinstance(info.clipfrac, float)
+    (coef[0] * loss.policy_loss + coef[1] * loss.value_loss + coef[2] * loss.entropy_loss).sum().backward()
+    torch.cuda.synchronize()
+    return [float(x.item()) for x in loss] + [info.approx_kl, info.clipfrac], host(ln.grad), host(vn.grad)
+
+
+def ppo_inputs(g, B, N, use_w):
+    lo = g.standard_normal((B, N)).astype(np.float32)
+    return dict(logits_new=(lo + 0.3 * g.standard_normal((B, N))).astype(np.float32), logits_old=lo,
+                action=g.integers(0, N, (B, )).astype(np.int64), value_new=g.standard_normal(B).astype(np.float32),
+                value_old=g.standard_normal(B).astype(np.float32), adv=g.standard_normal(B).astype(np.float32),
+                return_=g.standard_normal(B).astype(np.float32),
+                weight=g.random(B).astype(np.float32) if use_w else None)
+
+
+@pytest.mark.parametrize("B,N,use_w,clip,vclip,dual", [(128, 128, False, 0.2, True, None), (4096, 6, True, 0.2, True, 3.0),
+                                                         (17, 16, True, 0.1, False, None), (5, 1, False, 0.2, True, 2.0),
+                                                         (1000, 37, False, 0.3, False, 1.5), (300, 260, True, 0.2, True, None),
+                                                         (64, 1100, True, 0.2, True, 5.0), (70000, 8, True, 0.2, True, None)])
+def test_ppo_vs_oracle(B, N, use_w, clip, vclip, dual):
+    need_cuda()
+    inp = ppo_inputs(rng(B * 13 + N), B, N, use_w)
+    coef = [1.0, 0.5, -0.01]
+    outs, gl, gv = run_ppo(inp, clip, vclip, dual, coef)
+    o = orc.ppo(inp["logits_new"], inp["logits_old"], inp["action"], inp["value_new"], inp["value_old"], inp["adv"],
+                inp["return_"], inp["weight"], clip, vclip, dual, coef)
+    for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss", "approx_kl", "clipfrac")):
+        close(outs[k], o[nm], nm)
+    close(gl, o["grad_logits_new"], "grad_logits_new")
+    close(gv, o["grad_value_new"], "grad_value_new")
+
+
+@pytest.mark.parametrize("name", names("ppo"))
+def test_ppo_vs_golden(name):
+    need_cuda()
+    c = Case(name)
+    inp = {k: c.inp(k) for k in ("logits_new", "logits_old", "action", "value_new", "value_old", "adv", "return_",
+                                 "weight")}
+    coef = [c.attr("coef_policy"), c.attr("coef_value"), c.attr("coef_entropy")]
+    outs, gl, gv = run_ppo(inp, c.attr("clip_ratio"), bool(c.attr("use_value_clip")), c.attr("dual_clip"), coef)
+    for prec in (32, 64):
+        for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss")):
+            close(outs[k], c.out(nm, prec), nm)
+        close(gl, c.grad("logits_new", prec), "grad_logits_new")
+        close(gv, c.grad("value_new", prec), "grad_value_new")
+    close(outs[3], c.out("approx_kl", 32), "approx_kl")
+    close(outs[4], c.out("clipfrac", 32), "clipfrac")
+
+
+def test_ppo_dual_clip_must_exceed_one():
+    need_cuda()
+    from hpc_rll.rl_utils.ppo import PPO
+    inp = ppo_inputs(rng(1), 8, 4, False)
+    with pytest.raises(AssertionError):
+        PPO(8, 4)(*[dev(inp[k]) for k in ("logits_new", "logits_old", "action", "value_new", "value_old", "adv",
+                                          "return_")], None, 0.2, True, 0.5)
