@@ -84,13 +84,24 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd(const float* __restrict__ lo
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
     double acc[5] = {0, 0, 0, 0, 0};
+    constexpr bool PF = KMAX <= 2;  // software pipeline (see softmax_rows.cu)
+    Row rn, ro, nn, no;
+    int a, na = -1;
+    {
+        const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
+        rn.load(logits_new + row0 * N, N, G, lig, row0 < R);
+        ro.load(logits_old + row0 * N, N, G, lig, row0 < R);
+        a = row0 < R ? static_cast<int>(action[row0]) : -1;
+    }
     for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
         const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
         const bool active = row < R;
-        Row rn, ro;
-        rn.load(logits_new + row * N, N, G, lig, active);
-        ro.load(logits_old + row * N, N, G, lig, active);
-        const int a = active ? static_cast<int>(action[row]) : -1;
+        const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
+        if (PF) {
+            nn.load(logits_new + nrow * N, N, G, lig, nrow < R);
+            no.load(logits_old + nrow * N, N, G, lig, nrow < R);
+            na = nrow < R ? static_cast<int>(action[nrow]) : -1;
+        }
         float mn, sn, mo, so;
         rn.max_sumexp(G, mn, sn);
         ro.max_sumexp(G, mo, so);
@@ -121,6 +132,15 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd(const float* __restrict__ lo
                        weight ? weight[row] : 1.f, acc, pc, vc);
             pol_coef[row] = pc;
             val_coef[row] = vc;
+        }
+        if (PF) {
+            rn = nn;
+            ro = no;
+            a = na;
+        } else {
+            rn.load(logits_new + nrow * N, N, G, lig, nrow < R);
+            ro.load(logits_old + nrow * N, N, G, lig, nrow < R);
+            a = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
     }
     block_sum<5>(acc, red);

@@ -25,11 +25,18 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
     const int rows_per_block = rows_per_warp * 8;
     const float s1 = __ldg(g1);
     const float s2 = ENT ? __ldg(g2) * inv_n : 0.f;
+    // software pipeline: the next row block's loads are in flight while this one is reduced
+    constexpr bool PF = KMAX <= 2;
+    Row rr, nx;
+    {
+        const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
+        rr.load(logits + row0 * N, N, G, lig, row0 < R);
+    }
     for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
         const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
         const bool active = row < R;
-        Row rr;
-        rr.load(logits + row * N, N, G, lig, active);
+        const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
+        if (PF) nx.load(logits + nrow * N, N, G, lig, nrow < R);
         float m, s;
         rr.max_sumexp(G, m, s);
         const float logs = logf(s);
@@ -70,6 +77,8 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
                     st_stream(grad + row * N + e0, o[0]);
             }
         }
+        if (PF) rr = nx;
+        else rr.load(logits + nrow * N, N, G, lig, nrow < R);
     }
 }
 

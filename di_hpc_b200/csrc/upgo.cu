@@ -28,12 +28,22 @@ __global__ void __launch_bounds__(256) upgo_rows_fwd(const float* __restrict__ l
     const int lig = lane & (G - 1), gw = lane >> log2G;
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
+    constexpr bool PF = KMAX <= 2;  // software pipeline (see softmax_rows.cu)
+    Row rr, nx;
+    int a, na = -1;
+    {
+        const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
+        rr.load(logits + row0 * N, N, G, lig, row0 < R);
+        a = row0 < R ? static_cast<int>(action[row0]) : -1;
+    }
     for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
         const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
         const bool active = row < R;
-        Row rr;
-        rr.load(logits + row * N, N, G, lig, active);
-        const int a = active ? static_cast<int>(action[row]) : -1;
+        const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
+        if (PF) {
+            nx.load(logits + nrow * N, N, G, lig, nrow < R);
+            na = nrow < R ? static_cast<int>(action[nrow]) : -1;
+        }
         float m, s;
         rr.max_sumexp(G, m, s);
         const float logs = logf(s);
@@ -45,6 +55,13 @@ __global__ void __launch_bounds__(256) upgo_rows_fwd(const float* __restrict__ l
                 if (rr.index(j, q, G, lig) == a) sel = row_logp<false>(rr.x[j * W + q], m, logs);
         sel = group_sum(sel, G);
         if (active && lig == 0) metric[row] = sel;
+        if (PF) {
+            rr = nx;
+            a = na;
+        } else {
+            rr.load(logits + nrow * N, N, G, lig, nrow < R);
+            a = nrow < R ? static_cast<int>(action[nrow]) : -1;
+        }
     }
 }
 

@@ -40,13 +40,25 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
     double ent_acc = 0.0;
+    // software pipeline: next row block's loads are issued before this block is reduced
+    constexpr bool PF = KMAX <= 2;
+    Row rt, rbh, nt, nb;
+    int a, na = -1;
+    {
+        const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
+        rt.load(target + row0 * N, N, G, lig, row0 < R);
+        rbh.load(behaviour + row0 * N, N, G, lig, row0 < R);
+        a = row0 < R ? static_cast<int>(action[row0]) : -1;
+    }
     for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
         const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
         const bool active = row < R;
-        Row rt, rbh;
-        rt.load(target + row * N, N, G, lig, active);
-        rbh.load(behaviour + row * N, N, G, lig, active);
-        const int a = active ? static_cast<int>(action[row]) : -1;
+        const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
+        if (PF) {
+            nt.load(target + nrow * N, N, G, lig, nrow < R);
+            nb.load(behaviour + nrow * N, N, G, lig, nrow < R);
+            na = nrow < R ? static_cast<int>(action[nrow]) : -1;
+        }
         float mt, st, mb, sb;
         rt.max_sumexp(G, mt, st);
         rbh.max_sumexp(G, mb, sb);
@@ -75,6 +87,15 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__
             is_out[row] = expf(selt - selb);
             logp_out[row] = selt;
             ent_acc += static_cast<double>(H * (weight ? weight[row] : 1.f));
+        }
+        if (PF) {
+            rt = nt;
+            rbh = nb;
+            a = na;
+        } else {
+            rt.load(target + nrow * N, N, G, lig, nrow < R);
+            rbh.load(behaviour + nrow * N, N, G, lig, nrow < R);
+            a = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
     }
     double v[1] = {ent_acc};

@@ -21,6 +21,7 @@ from hpc_rll.rl_utils.upgo import UPGO  # noqa: E402
 from hpc_rll.rl_utils.vtrace import VTrace  # noqa: E402
 
 DEV = "cuda"
+ONE = None  # ones(1) on the device, set in main()
 
 
 def peak():
@@ -62,7 +63,7 @@ def rnd(*shape):
 def bench_gae(T, B, iters):
     v, r, g = rnd(T + 1, B).requires_grad_(True), rnd(T, B).requires_grad_(True), rnd(T, B)
     m = GAE(T, B)
-    f, b, L = timed(lambda: m(v, r), lambda o: torch.autograd.backward(o, g, inputs=[v, r]), iters)
+    f, b, L = timed(lambda: m(v, r), lambda o: torch.autograd.grad(o, [v, r], grad_outputs=g), iters)
     return dict(op="gae", shape=dict(T=T, B=B), units=T * B, unit="steps", alg_bytes=24 * T * B + 8 * B, fwd_ms=f,
                 bwd_ms=b, launches=L)
 
@@ -71,7 +72,7 @@ def bench_td_lambda(T, B, iters, use_w=True):
     v, r = rnd(T + 1, B).requires_grad_(True), rnd(T, B)
     w = torch.rand(T, B, device=DEV) if use_w else None
     m = TDLambda(T, B)
-    f, b, L = timed(lambda: m(v, r, w), lambda o: torch.autograd.backward(o.sum(), inputs=[v]), iters)
+    f, b, L = timed(lambda: m(v, r, w), lambda o: torch.autograd.grad(o, [v], grad_outputs=ONE), iters)
     return dict(op="td_lambda" + ("_w" if use_w else ""), shape=dict(T=T, B=B), units=T * B, unit="steps",
                 alg_bytes=(24 if use_w else 20) * T * B, fwd_ms=f, bwd_ms=b, launches=L)
 
@@ -88,7 +89,7 @@ def bench_vtrace(T, B, N, iters, use_w=False):
         l = m(t, bh, a, v, r, w)
         return l.policy_loss + l.value_loss + l.entropy_loss
 
-    f, b, L = timed(fwd, lambda o: torch.autograd.backward(o.sum(), inputs=[t, v]), iters)
+    f, b, L = timed(fwd, lambda o: torch.autograd.grad(o, [t, v], grad_outputs=ONE), iters)
     return dict(op="vtrace", shape=dict(T=T, B=B, N=N), units=T * B, unit="steps",
                 alg_bytes=(16 * N + 52 + (8 if use_w else 0)) * T * B, fwd_ms=f, bwd_ms=b, launches=L)
 
@@ -99,7 +100,7 @@ def bench_upgo(T, B, N, iters):
     a = torch.randint(0, N, (T, B), device=DEV)
     r, v = rnd(T, B), rnd(T + 1, B)
     m = UPGO(T, B, N)
-    f, b, L = timed(lambda: m(t, rho, a, r, v), lambda o: torch.autograd.backward(o.sum(), inputs=[t]), iters)
+    f, b, L = timed(lambda: m(t, rho, a, r, v), lambda o: torch.autograd.grad(o, [t], grad_outputs=ONE), iters)
     return dict(op="upgo", shape=dict(T=T, B=B, N=N), units=T * B, unit="steps", alg_bytes=(12 * N + 36) * T * B,
                 fwd_ms=f, bwd_ms=b, launches=L)
 
@@ -116,7 +117,7 @@ def bench_ppo(B, N, iters):
         l, _ = m(ln, lo, a, vn, vo, adv, ret)
         return l.policy_loss + l.value_loss + l.entropy_loss
 
-    f, b, L = timed(fwd, lambda o: torch.autograd.backward(o.sum(), inputs=[ln, vn]), iters)
+    f, b, L = timed(fwd, lambda o: torch.autograd.grad(o, [ln, vn], grad_outputs=ONE), iters)
     return dict(op="ppo", shape=dict(B=B, N=N), units=B, unit="samples", alg_bytes=(16 * N + 50) * B, fwd_ms=f,
                 bwd_ms=b, launches=L)
 
@@ -131,7 +132,7 @@ def bench_q(T, B, N, iters, rescale=False):
     a, an, r, d = nstep_common(T, B, N)
     m = (QNStepTDRescale if rescale else QNStepTD)(T, B, N)
     f, b, L = timed(lambda: m(q, nq, a, an, r, d, None, 0.99)[0],
-                    lambda o: torch.autograd.backward(o.sum(), inputs=[q]), iters)
+                    lambda o: torch.autograd.grad(o, [q], grad_outputs=ONE), iters)
     return dict(op="q_nstep_td" + ("_rescale" if rescale else ""), shape=dict(T=T, B=B, N=N), units=B, unit="samples",
                 alg_bytes=(4 * T + 4 * N + 100) * B, fwd_ms=f, bwd_ms=b, launches=L)
 
@@ -142,7 +143,7 @@ def bench_dist(T, B, N, n_atom, iters):
     a, an, r, d = nstep_common(T, B, N)
     m = DistNStepTD(T, B, N, n_atom)
     f, b, L = timed(lambda: m(d0, d1, a, an, r, d, None, 0.99, -10.0, 10.0)[0],
-                    lambda o: torch.autograd.backward(o.sum(), inputs=[d0]), iters)
+                    lambda o: torch.autograd.grad(o, [d0], grad_outputs=ONE), iters)
     return dict(op="dist_nstep_td", shape=dict(T=T, B=B, N=N, n_atom=n_atom), units=B, unit="samples",
                 alg_bytes=(8 * n_atom + 4 * T + 30 + 4 * N * n_atom + 4 * n_atom) * B, fwd_ms=f, bwd_ms=b, launches=L)
 
@@ -151,7 +152,7 @@ def bench_qrdqn(tau, T, B, N, iters):
     q, nq = rnd(B, N, tau).requires_grad_(True), rnd(B, N, tau)
     a, an, r, d = nstep_common(T, B, N)
     m = QRDQNNStepTDError(tau, T, B, N)
-    f, b, L = timed(lambda: m(q, nq, a, an, r, d, 0.99)[0], lambda o: torch.autograd.backward(o.sum(), inputs=[q]),
+    f, b, L = timed(lambda: m(q, nq, a, an, r, d, 0.99)[0], lambda o: torch.autograd.grad(o, [q], grad_outputs=ONE),
                     iters)
     return dict(op="qrdqn_nstep_td", shape=dict(tau=tau, T=T, B=B, N=N), units=B, unit="samples",
                 alg_bytes=(8 * tau + 4 * N * tau + 4 * T + 32) * B, pair_flops=tau * tau * 12 * B, fwd_ms=f, bwd_ms=b,
@@ -164,7 +165,7 @@ def bench_iqn(tau, tau_p, T, B, N, iters):
     rq = torch.rand(tau, B, device=DEV)
     m = IQNNStepTDError(tau, tau_p, T, B, N)
     f, b, L = timed(lambda: m(q, nq, a, an, r, d, rq, 0.99, 1.0)[0],
-                    lambda o: torch.autograd.backward(o.sum(), inputs=[q]), iters)
+                    lambda o: torch.autograd.grad(o, [q], grad_outputs=ONE), iters)
     # gathers touch one 32 B sector per (quantile, sample): min(4N, 32) B each
     sect = max(32, 4) if N <= 8 else 32
     return dict(op="iqn_nstep_td", shape=dict(tau=tau, tau_p=tau_p, T=T, B=B, N=N), units=B, unit="samples",
@@ -178,6 +179,8 @@ def main():
     ap.add_argument("--ops", default="all")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
+    global ONE
+    ONE = torch.ones(1, device=DEV)
     it = 5 if args.quick else 20
     sel = None if args.ops == "all" else set(args.ops.split(","))
     pk = peak()
