@@ -77,7 +77,6 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd(const float* __restrict__ lo
                                                      float* __restrict__ val_coef, double* __restrict__ partials,
                                                      const PpoParams P, int64_t R, int N, int G, int log2G) {
     using Row = RowRegs<KMAX, VEC>;
-    constexpr int W = Row::W;
     __shared__ double red[5 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (G - 1), gw = lane >> log2G;
@@ -102,30 +101,14 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd(const float* __restrict__ lo
             no.load(logits_old + nrow * N, N, G, lig, nrow < R);
             na = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
-        float mn, sn, mo, so;
-        rn.max_sumexp(G, mn, sn);
-        ro.max_sumexp(G, mo, so);
+        const float mn = rn.row_max(G), mo = ro.row_max(G);
+        float sn, tn, so, to, none[Row::NE];
+        rn.template stats<true, false>(G, mn, sn, tn, none);
+        ro.template stats<false, false>(G, mo, so, to, none);
         const float lsn = logf(sn), lso = logf(so);
-        float hpart = 0.f, seln = 0.f, selo = 0.f;
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-#pragma unroll
-            for (int q = 0; q < W; ++q) {
-                const int i = j * W + q;
-                const int idx = rn.index(j, q, G, lig);
-                if (idx < N) {
-                    const float lp = row_logp<true>(rn.x[i], mn, lsn);
-                    hpart += expf(lp) * lp;
-                    if (idx == a) {
-                        seln = lp;
-                        selo = row_logp<true>(ro.x[i], mo, lso);
-                    }
-                }
-            }
-        }
-        const float H = -group_sum(hpart, G);
-        seln = group_sum(seln, G);
-        selo = group_sum(selo, G);
+        const float H = lsn - tn / sn;
+        const float seln = row_logp<true>(group_sum(rn.select(a, G, lig), G), mn, lsn);
+        const float selo = row_logp<true>(group_sum(ro.select(a, G, lig), G), mo, lso);
         if (active && lig == 0) {
             float pc, vc;
             ppo_sample(P, seln, selo, H, adv[row], value_new[row], value_old[row], ret[row],
@@ -244,15 +227,8 @@ int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const 
     if (ge.kmax == 0)
         ppo_rows_fwd_loop<<<grid, 256, 0, stream>>>(logits_new, logits_old, action, value_new, value_old, adv, return_,
                                                     weight, pol_coef, val_coef, partials, P, B, n);
-    else if (ge.vec) {
-        if (ge.kmax == 1) HPC_PPO_ROWS(1, true);
-        else if (ge.kmax == 2) HPC_PPO_ROWS(2, true);
-        else HPC_PPO_ROWS(8, true);
-    } else {
-        if (ge.kmax == 1) HPC_PPO_ROWS(1, false);
-        else if (ge.kmax == 2) HPC_PPO_ROWS(2, false);
-        else HPC_PPO_ROWS(8, false);
-    }
+    else
+        HPC_ROW_DISPATCH(ge, HPC_PPO_ROWS);
 #undef HPC_PPO_ROWS
     count_launch();
     HPC_LAUNCH_CHECK();

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
     const int rows_per_block = rows_per_warp * 8;
     const float s1 = __ldg(g1);
     const float s2 = ENT ? __ldg(g2) * inv_n : 0.f;
-    // software pipeline: the next row block's loads are in flight while this one is reduced
+    // software pipeline (small rows only): the next row block's loads fly while this one is reduced
     constexpr bool PF = KMAX <= 2;
     Row rr, nx;
     {
@@ -37,26 +37,14 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
         const bool active = row < R;
         const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
         if (PF) nx.load(logits + nrow * N, N, G, lig, nrow < R);
-        float m, s;
-        rr.max_sumexp(G, m, s);
-        const float logs = logf(s);
         const int a = active ? static_cast<int>(action[row]) : -1;
         const float c = active ? s1 * c1[row] : 0.f;
         const float e2 = ENT ? s2 * ((w && active) ? w[row] : 1.f) : 0.f;
-        float lp[Row::NE], p[Row::NE];
-        float hpart = 0.f;
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-#pragma unroll
-            for (int q = 0; q < W; ++q) {
-                const int i = j * W + q;
-                const bool ok = rr.index(j, q, G, lig) < N;
-                lp[i] = row_logp<CAT>(rr.x[i], m, logs);
-                p[i] = ok ? expf(lp[i]) : 0.f;
-                if (ENT && ok) hpart += p[i] * lp[i];
-            }
-        }
-        const float H = ENT ? -group_sum(hpart, G) : 0.f;
+        const float m = rr.row_max(G);
+        float s, t, e[Row::NE];
+        rr.template stats<ENT, true>(G, m, s, t, e);
+        const float logs = logf(s), inv_s = 1.f / s;
+        const float H = logs - t * inv_s;  // = -sum p log p
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
             float o[W];
@@ -64,8 +52,9 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
             for (int q = 0; q < W; ++q) {
                 const int i = j * W + q;
                 const int idx = rr.index(j, q, G, lig);
-                float gq = c * ((idx == a ? 1.f : 0.f) - p[i]);
-                if (ENT) gq += e2 * (-p[i] * (lp[i] + H));
+                const float p = e[i] * inv_s;
+                float gq = c * ((idx == a ? 1.f : 0.f) - p);
+                if (ENT) gq += e2 * (-p * (fmaxf(row_logp<CAT>(rr.x[i], m, logs), kNegBig) + H));
                 o[q] = gq;
             }
             const int e0 = rr.index(j, 0, G, lig);
@@ -140,15 +129,8 @@ static int launch_grad_t(const float* logits, const int64_t* action, const float
     if (ge.kmax == 0)
         softmax_grad_rows_loop_kernel<ENT, CAT><<<grid, 256, 0, stream>>>(logits, action, c1, w, g1, g2, inv_n, grad,
                                                                          R, N);
-    else if (ge.vec) {
-        if (ge.kmax == 1) HPC_GRAD_LAUNCH(1, true);
-        else if (ge.kmax == 2) HPC_GRAD_LAUNCH(2, true);
-        else HPC_GRAD_LAUNCH(8, true);
-    } else {
-        if (ge.kmax == 1) HPC_GRAD_LAUNCH(1, false);
-        else if (ge.kmax == 2) HPC_GRAD_LAUNCH(2, false);
-        else HPC_GRAD_LAUNCH(8, false);
-    }
+    else
+        HPC_ROW_DISPATCH(ge, HPC_GRAD_LAUNCH);
 #undef HPC_GRAD_LAUNCH
     count_launch();
     HPC_LAUNCH_CHECK();

@@ -23,7 +23,6 @@ __global__ void __launch_bounds__(256) upgo_rows_fwd(const float* __restrict__ l
                                                       float* __restrict__ metric, int64_t R, int N, int G,
                                                       int log2G) {
     using Row = RowRegs<KMAX, VEC>;
-    constexpr int W = Row::W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (G - 1), gw = lane >> log2G;
     const int rows_per_warp = 32 >> log2G;
@@ -44,16 +43,10 @@ __global__ void __launch_bounds__(256) upgo_rows_fwd(const float* __restrict__ l
             nx.load(logits + nrow * N, N, G, lig, nrow < R);
             na = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
-        float m, s;
-        rr.max_sumexp(G, m, s);
-        const float logs = logf(s);
-        float sel = 0.f;
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j)
-#pragma unroll
-            for (int q = 0; q < W; ++q)
-                if (rr.index(j, q, G, lig) == a) sel = row_logp<false>(rr.x[j * W + q], m, logs);
-        sel = group_sum(sel, G);
+        const float m = rr.row_max(G);
+        float s, t, none[Row::NE];
+        rr.template stats<false, false>(G, m, s, t, none);
+        const float sel = row_logp<false>(group_sum(rr.select(a, G, lig), G), m, logf(s));
         if (active && lig == 0) metric[row] = sel;
         if (PF) {
             rr = nx;
@@ -221,15 +214,7 @@ int hpc_rll_upgo_forward(const float* target_output, const float* rhos, const in
     const int n = static_cast<int>(N);
 #define HPC_UP_ROWS(K, V) upgo_rows_fwd<K, V><<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n, ge.G, log2G)
     if (ge.kmax == 0) upgo_rows_fwd_loop<<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n);
-    else if (ge.vec) {
-        if (ge.kmax == 1) HPC_UP_ROWS(1, true);
-        else if (ge.kmax == 2) HPC_UP_ROWS(2, true);
-        else HPC_UP_ROWS(8, true);
-    } else {
-        if (ge.kmax == 1) HPC_UP_ROWS(1, false);
-        else if (ge.kmax == 2) HPC_UP_ROWS(2, false);
-        else HPC_UP_ROWS(8, false);
-    }
+    else HPC_ROW_DISPATCH(ge, HPC_UP_ROWS);
 #undef HPC_UP_ROWS
     count_launch();
     HPC_LAUNCH_CHECK();

@@ -33,7 +33,6 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__
                                                         float* __restrict__ logp_out, double* __restrict__ partials,
                                                         int64_t R, int N, int G, int log2G) {
     using Row = RowRegs<KMAX, VEC>;
-    constexpr int W = Row::W;
     __shared__ double red[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (G - 1), gw = lane >> log2G;
@@ -59,30 +58,15 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__
             nb.load(behaviour + nrow * N, N, G, lig, nrow < R);
             na = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
-        float mt, st, mb, sb;
-        rt.max_sumexp(G, mt, st);
-        rbh.max_sumexp(G, mb, sb);
+        const float mt = rt.row_max(G), mb = rbh.row_max(G);
+        float st, tt, sb, tb, none[Row::NE];
+        rt.template stats<true, false>(G, mt, st, tt, none);
+        rbh.template stats<false, false>(G, mb, sb, tb, none);
         const float lst = logf(st), lsb = logf(sb);
-        float hpart = 0.f, selt = 0.f, selb = 0.f;
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-#pragma unroll
-            for (int q = 0; q < W; ++q) {
-                const int i = j * W + q;
-                const int idx = rt.index(j, q, G, lig);
-                if (idx < N) {
-                    const float lp = row_logp<true>(rt.x[i], mt, lst);
-                    hpart += expf(lp) * lp;
-                    if (idx == a) {
-                        selt = lp;
-                        selb = row_logp<true>(rbh.x[i], mb, lsb);
-                    }
-                }
-            }
-        }
-        const float H = -group_sum(hpart, G);
-        selt = group_sum(selt, G);  // exactly one lane of the group holds the action's entry
-        selb = group_sum(selb, G);
+        const float H = lst - tt / st;  // entropy of the target policy
+        // exactly one lane of the group holds the action's logit
+        const float selt = row_logp<true>(group_sum(rt.select(a, G, lig), G), mt, lst);
+        const float selb = row_logp<true>(group_sum(rbh.select(a, G, lig), G), mb, lsb);
         if (active && lig == 0) {
             is_out[row] = expf(selt - selb);
             logp_out[row] = selt;
@@ -339,15 +323,8 @@ int hpc_rll_vtrace_forward(const float* target_output, const float* behaviour_ou
     if (ge.kmax == 0)
         vtrace_rows_fwd_loop<<<grid1, 256, 0, stream>>>(target_output, behaviour_output, action, weight, is_buf,
                                                         logp_buf, partials, R, n);
-    else if (ge.vec) {
-        if (ge.kmax == 1) HPC_VT_ROWS(1, true);
-        else if (ge.kmax == 2) HPC_VT_ROWS(2, true);
-        else HPC_VT_ROWS(8, true);
-    } else {
-        if (ge.kmax == 1) HPC_VT_ROWS(1, false);
-        else if (ge.kmax == 2) HPC_VT_ROWS(2, false);
-        else HPC_VT_ROWS(8, false);
-    }
+    else
+        HPC_ROW_DISPATCH(ge, HPC_VT_ROWS);
 #undef HPC_VT_ROWS
     count_launch();
     HPC_LAUNCH_CHECK();
