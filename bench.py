@@ -298,7 +298,7 @@ def run_ours(args):
     d2h = 4 * (T * B + (T + 1) * B + T * B)
     e2e = {"value": T * B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": Ke,
-           "api": "hpc_rll_gae_fwd_bwd_host (pinned host buffers, 3-slot column-block pipeline)"}
+           "api": "hpc_rll_gae_fwd_bwd_host (pinned host buffers, 4-slot column-block pipeline)"}
 
     if rank == 0:
         base, _ = cpu_baseline(T, B, 5) if world == 1 else (None, None)

@@ -318,7 +318,8 @@ static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab,
 //   0: BT=64  TT=16 ST=3      1: BT=128 TT=16 ST=3     2: BT=32 TT=32 ST=3
 //   3: BT=64  TT=32 ST=3      4: BT=128 TT=8  ST=4     5: BT=64 TT=8  ST=6
 //   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     8: BT=256 TT=16 ST=3
-//  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     99: generic (non-TMA) kernel
+//  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     13: BT=32 TT=64 ST=6   14: BT=32 TT=16 ST=12
+//  99: generic (non-TMA) kernel
 // (a TMA box dimension is limited to 256 elements, so BT <= 256)
 static int pick_cfg(int64_t B) {
     const int forced = tuning_config(HPC_RLL_OP_GAE);
@@ -356,6 +357,8 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
         case 8: return launch_fwd_tma<256, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         case 10: return launch_fwd_tma<256, 4, 8>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         case 11: return launch_fwd_tma<256, 8, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 13: return launch_fwd_tma<32, 64, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        case 14: return launch_fwd_tma<32, 16, 12>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         default: break;
     }
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);
@@ -396,6 +399,8 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
         case 8: return launch_bwd_tma<256, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         case 10: return launch_bwd_tma<256, 4, 8>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         case 11: return launch_bwd_tma<256, 8, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 13: return launch_bwd_tma<32, 64, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        case 14: return launch_bwd_tma<32, 16, 12>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         default: break;
     }
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);
@@ -411,7 +416,7 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct HostPipe {
-    static constexpr int kSlots = 3;
+    static constexpr int kSlots = 4;
     int dev = -1;
     cudaStream_t stream[kSlots] = {};
     float* buf[kSlots] = {};
@@ -430,8 +435,9 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
     std::lock_guard<std::mutex> lk(g_hp.mu);
     int dev = 0;
     HPC_CUDA(cudaGetDevice(&dev));
-    // column block: multiple of 128 columns, ~16 MB per tensor per slot
-    int64_t cb = (int64_t(4) << 20) / (T + 1);
+    // column block: multiple of 128 columns, ~8 MB per tensor per slot (32 blocks at T=1024, B=65536:
+    // pipeline fill/drain is ~1/32 of the copy time)
+    int64_t cb = (int64_t(2) << 20) / (T + 1);
     cb = (cb / 128) * 128;
     if (cb < 128) cb = 128;
     if (cb > B) cb = ((B + 3) / 4) * 4;
@@ -468,15 +474,19 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
         float* d_gadv = d_adv + per_tensor;
         float* d_gvalue = d_gadv + per_tensor;
         float* d_greward = d_gvalue + per_tensor;
+        // all host->device copies of the block first, then both kernels, then all device->host copies:
+        // the H2D and D2H copy engines then run back to back across the slots' streams
         HPC_CUDA(cudaMemcpy2DAsync(d_value, dp, h_value + c0, hp, wb, rows, cudaMemcpyHostToDevice, st));
         HPC_CUDA(cudaMemcpy2DAsync(d_reward, dp, h_reward + c0, hp, wb, rows - 1, cudaMemcpyHostToDevice, st));
+        if (bwd) HPC_CUDA(cudaMemcpy2DAsync(d_gadv, dp, h_gadv + c0, hp, wb, rows - 1, cudaMemcpyHostToDevice, st));
         int rc = gae_forward_impl(d_value, cb, d_reward, cb, d_adv, cb, T, w, gamma, lambda, st);
         if (rc) return rc;
-        HPC_CUDA(cudaMemcpy2DAsync(h_adv + c0, hp, d_adv, dp, wb, rows - 1, cudaMemcpyDeviceToHost, st));
         if (bwd) {
-            HPC_CUDA(cudaMemcpy2DAsync(d_gadv, dp, h_gadv + c0, hp, wb, rows - 1, cudaMemcpyHostToDevice, st));
             rc = gae_backward_impl(d_gadv, cb, d_gvalue, cb, d_greward, cb, T, w, gamma, lambda, st);
             if (rc) return rc;
+        }
+        HPC_CUDA(cudaMemcpy2DAsync(h_adv + c0, hp, d_adv, dp, wb, rows - 1, cudaMemcpyDeviceToHost, st));
+        if (bwd) {
             HPC_CUDA(cudaMemcpy2DAsync(h_gvalue + c0, hp, d_gvalue, dp, wb, rows, cudaMemcpyDeviceToHost, st));
             HPC_CUDA(cudaMemcpy2DAsync(h_greward + c0, hp, d_greward, dp, wb, rows - 1, cudaMemcpyDeviceToHost, st));
         }

@@ -54,7 +54,7 @@ def test_gae_vs_golden(name):
     assert rel_err(gr, c.grad("reward", 64)) <= 1e-5
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 99])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 13, 14, 99])
 def test_gae_every_kernel_config(cfg):
     """All tile configurations (and the non-TMA kernel) must give identical bits."""
     need_cuda()
