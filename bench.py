@@ -34,6 +34,7 @@ if ROOT not in sys.path:
 
 T_DEFAULT, B_DEFAULT = 1024, 65536
 GAMMA, LAMBDA = 0.99, 0.97
+OUT = sys.stdout
 METRIC = "gae_fwd_bwd_trajectory_steps_per_sec"
 UNIT = "steps/s"
 
@@ -163,7 +164,7 @@ def run_reference(args):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=OUT, flush=True)
 
 
 def run_ours(args):
@@ -312,10 +313,20 @@ def run_ours(args):
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         if base is not None:
             line["cpu_baseline"] = base
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=OUT, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """The driver parses ONE JSON line from stdout.  Libraries (NCCL's version banner, torchrun notices)
+    also write there, so stdout is pointed at stderr for the whole run and the JSON line goes to the
+    saved descriptor."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 def main():
@@ -327,10 +338,13 @@ def main():
     ap.add_argument("--T", type=int, default=T_DEFAULT)
     ap.add_argument("--B", type=int, default=B_DEFAULT, help="columns per GPU")
     args = ap.parse_args()
+    global OUT
+    OUT = _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    OUT.flush()
 
 
 if __name__ == "__main__":
