@@ -272,6 +272,137 @@ __global__ void __launch_bounds__(128) gae_bwd_generic(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// T-split kernels for the small-batch regime (few columns, long T: e.g. the reference's own test shape
+// T=1024, B=64, tests/test_gae.py:10-11).  With only B/32 warps of work the column scan is latency
+// bound, so T is cut into S segments that run in parallel (grid = column tiles x S):
+//   pass 1: every segment scans its rows from a zero carry and publishes its aggregate
+//           (the recurrence is affine with constant coefficient a = gamma*lambda, so a segment of
+//            length L maps carry c to  g_loc + a^L * c; only g_loc needs storing)
+//   pass 2: every segment composes the aggregates of the segments it depends on (Horner, <= S-1
+//           fused multiply-adds on values that sit in L2), then re-scans its rows with the true carry
+//           and writes the outputs.
+// Inputs are read twice, but in this regime they live in L2 (T*B*12 bytes << 126 MB).  Re-association
+// means results agree with the serial scan to ~1e-7 relative rather than bit for bit; the large-batch
+// TMA path above stays bit-exact.  SURVEY.md 8(f) item 2.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSplitThreads = 64;
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kSplitThreads) gae_fwd_split(const float* __restrict__ value, int64_t ldv,
+                                                                const float* __restrict__ reward, int64_t ldr,
+                                                                const float* __restrict__ dtab,
+                                                                float* __restrict__ agg, float* __restrict__ adv,
+                                                                int64_t lda, int T, int B, int seg_len, float gamma,
+                                                                float factor) {
+    const int col = blockIdx.x * kSplitThreads + threadIdx.x;
+    const int s = blockIdx.y, S = gridDim.y;
+    if (col >= B) return;
+    const int t0 = s * seg_len, t1 = min(T, t0 + seg_len);
+    if (t0 >= T) {
+        if (!WRITE) agg[static_cast<int64_t>(s) * B + col] = 0.f;
+        return;
+    }
+    float g = 0.f;
+    if (WRITE) {  // carry from the later segments: G = B_k + a^{len_k} * G, k = S-1 .. s+1
+        for (int k = S - 1; k > s; --k) {
+            const int len_k = min(T, (k + 1) * seg_len) - min(T, k * seg_len);
+            g = fmaf(powf(factor, static_cast<float>(len_k)), g, __ldcg(agg + static_cast<int64_t>(k) * B + col));
+        }
+    }
+    GaeFwdBody body;
+    body.valid = WRITE;
+    body.g = g;
+    body.gamma = gamma;
+    body.factor = factor;
+    body.ld = lda;
+    body.adv = adv + static_cast<int64_t>(t1 - 1) * lda + col;
+    body.v1 = __ldg(value + static_cast<int64_t>(t1) * ldv + col);
+    constexpr int U = 8;
+    int t = t1 - 1;
+    for (; t - (U - 1) >= t0; t -= U) {
+        float v[U], r[U];
+        float2 d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            v[u] = __ldg(value + static_cast<int64_t>(t - u) * ldv + col);
+            r[u] = __ldg(reward + static_cast<int64_t>(t - u) * ldr + col);
+            d[u] = __ldg(reinterpret_cast<const float2*>(dtab) + t - u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float x[2] = {v[u], r[u]};
+            const float dt[2] = {d[u].x, d[u].y};
+            body.step(t - u, x, dt);
+        }
+    }
+    for (; t >= t0; --t) {
+        const float x[2] = {__ldg(value + static_cast<int64_t>(t) * ldv + col),
+                            __ldg(reward + static_cast<int64_t>(t) * ldr + col)};
+        const float2 d = __ldg(reinterpret_cast<const float2*>(dtab) + t);
+        const float dt[2] = {d.x, d.y};
+        body.step(t, x, dt);
+    }
+    if (!WRITE) agg[static_cast<int64_t>(s) * B + col] = body.g;
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kSplitThreads) gae_bwd_split(const float* __restrict__ grad_adv, int64_t ldg,
+                                                                const float* __restrict__ dtab,
+                                                                float* __restrict__ agg,
+                                                                float* __restrict__ grad_value, int64_t ldgv,
+                                                                float* __restrict__ grad_reward, int64_t ldgr, int T,
+                                                                int B, int seg_len, float gamma, float factor) {
+    const int col = blockIdx.x * kSplitThreads + threadIdx.x;
+    const int s = blockIdx.y;
+    if (col >= B) return;
+    const int t0 = s * seg_len, t1 = min(T, t0 + seg_len);
+    if (t0 >= T) {
+        if (!WRITE) agg[static_cast<int64_t>(s) * B + col] = 0.f;
+        return;
+    }
+    float gh = 0.f;
+    if (WRITE) {  // carry from the earlier segments: ghat = agg_k + a^{len_k} * ghat, k = 0 .. s-1
+        for (int k = 0; k < s; ++k)
+            gh = fmaf(powf(factor, static_cast<float>(seg_len)), gh, __ldcg(agg + static_cast<int64_t>(k) * B + col));
+    }
+    GaeBwdBody body;
+    body.valid = WRITE;
+    body.gh = gh;
+    body.prev = t0 > 0 ? __fmul_rn(__ldg(dtab + 2 * (t0 - 1)), gh) : 0.f;  // dd_{t0-1} = d_{t0-1} * ghat_{t0-1}
+    body.gamma = gamma;
+    body.factor = factor;
+    body.gv = grad_value + static_cast<int64_t>(t0) * ldgv + col;
+    body.gr = grad_reward + static_cast<int64_t>(t0) * ldgr + col;
+    body.ld_gv = ldgv;
+    body.ld_gr = ldgr;
+    constexpr int U = 8;
+    int t = t0;
+    for (; t + U <= t1; t += U) {
+        float g[U];
+        float2 d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            g[u] = __ldg(grad_adv + static_cast<int64_t>(t + u) * ldg + col);
+            d[u] = __ldg(reinterpret_cast<const float2*>(dtab) + t + u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float x[1] = {g[u]};
+            const float dt[2] = {d[u].x, d[u].y};
+            body.step(t + u, x, dt);
+        }
+    }
+    for (; t < t1; ++t) {
+        const float x[1] = {__ldg(grad_adv + static_cast<int64_t>(t) * ldg + col)};
+        const float2 d = __ldg(reinterpret_cast<const float2*>(dtab) + t);
+        const float dt[2] = {d.x, d.y};
+        body.step(t, x, dt);
+    }
+    if (!WRITE) agg[static_cast<int64_t>(s) * B + col] = body.gh;
+    else if (t1 == T) *body.gv = __fmul_rn(gamma, body.prev);  // row T
+}
+
+// ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
 
@@ -319,7 +450,7 @@ static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab,
 //   3: BT=64  TT=32 ST=3      4: BT=128 TT=8  ST=4     5: BT=64 TT=8  ST=6
 //   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     8: BT=256 TT=16 ST=3
 //  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     13: BT=32 TT=64 ST=6   14: BT=32 TT=16 ST=12
-//  99: generic (non-TMA) kernel
+//  20: T-split (small batch; automatic for B <= 2048 and T >= 128)   99: generic (non-TMA) kernel
 // (a TMA box dimension is limited to 256 elements, so BT <= 256)
 static int pick_cfg(int64_t B) {
     const int forced = tuning_config(HPC_RLL_OP_GAE);
@@ -329,6 +460,64 @@ static int pick_cfg(int64_t B) {
     if (B >= 128 * sms) return 1;
     if (B >= 64 * sms) return 0;
     return 2;
+}
+
+// T-split geometry: S segments of seg_len rows so that tiles*S covers the machine about twice
+static bool split_geometry(int64_t T, int64_t B, int* S, int* seg_len) {
+    const int forced = tuning_config(HPC_RLL_OP_GAE);
+    if (forced >= 0 && forced != 20) return false;
+    if (forced < 0 && !(B <= 2048 && T >= 128)) return false;
+    const int64_t tiles = (B + kSplitThreads - 1) / kSplitThreads;
+    int64_t s = (2 * static_cast<int64_t>(sm_count()) + tiles - 1) / tiles;
+    if (s > 32) s = 32;
+    if (s > T / 16) s = T / 16;
+    if (s < 2) return false;
+    int64_t len = (T + s - 1) / s;
+    len = (len + 7) / 8 * 8;
+    *seg_len = static_cast<int>(len);
+    *S = static_cast<int>((T + len - 1) / len);
+    return *S >= 2;
+}
+
+// scratch for the segment aggregates: S*B floats, cached per device and grown on demand.  Launches that
+// share it are ordered by the stream they run on; concurrent use from several streams of one device is
+// serialised by an event.
+namespace {
+struct SplitScratch {
+    float* buf = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+};
+std::mutex g_split_mu;
+std::map<int, SplitScratch> g_split;
+}  // namespace
+
+// inside CUDA-graph capture the cross-stream event handshake is skipped (a graph replays on one stream
+// in order; warm up once before capturing so the scratch exists)
+static bool stream_capturing(cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+}
+
+static int split_scratch(size_t floats, cudaStream_t stream, SplitScratch** out) {
+    int dev = 0;
+    HPC_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_split_mu);
+    SplitScratch& sc = g_split[dev];
+    if (!sc.done) HPC_CUDA(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
+    if (sc.cap < floats) {
+        if (sc.buf) {
+            HPC_CUDA(cudaDeviceSynchronize());
+            cudaFree(sc.buf);
+        }
+        const size_t want = floats < (size_t(1) << 18) ? (size_t(1) << 18) : floats;
+        HPC_CUDA(cudaMalloc(&sc.buf, want * sizeof(float)));
+        sc.cap = want;
+    } else if (!stream_capturing(stream)) {
+        HPC_CUDA(cudaStreamWaitEvent(stream, sc.done, 0));  // previous user (possibly another stream) is done
+    }
+    *out = &sc;
+    return HPC_RLL_OK;
 }
 
 static int gae_forward_impl(const float* value, int64_t ldv, const float* reward, int64_t ldr, float* adv,
@@ -342,6 +531,21 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
     int rc = get_dtab(T, lambda, &dtab);
     if (rc) return rc;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
+    int S = 0, seg_len = 0;
+    if (split_geometry(T, B, &S, &seg_len)) {
+        SplitScratch* sc = nullptr;
+        rc = split_scratch(static_cast<size_t>(S) * static_cast<size_t>(B), stream, &sc);
+        if (rc) return rc;
+        const dim3 grid(static_cast<unsigned>((B + kSplitThreads - 1) / kSplitThreads), static_cast<unsigned>(S));
+        gae_fwd_split<false><<<grid, kSplitThreads, 0, stream>>>(value, ldv, reward, ldr, dtab, sc->buf, adv, lda,
+                                                                 static_cast<int>(T), static_cast<int>(B), seg_len, g, f);
+        gae_fwd_split<true><<<grid, kSplitThreads, 0, stream>>>(value, ldv, reward, ldr, dtab, sc->buf, adv, lda,
+                                                                static_cast<int>(T), static_cast<int>(B), seg_len, g, f);
+        count_launch(2);
+        HPC_LAUNCH_CHECK();
+        if (!stream_capturing(stream)) HPC_CUDA(cudaEventRecord(sc->done, stream));
+        return HPC_RLL_OK;
+    }
     int cfg = pick_cfg(B);
     const bool tma = tma_ok_2d(value, B, ldv) && tma_ok_2d(reward, B, ldr);
     if (!tma) cfg = 99;
@@ -385,6 +589,21 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
     int rc = get_dtab(T, lambda, &dtab);
     if (rc) return rc;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
+    int S = 0, seg_len = 0;
+    if (split_geometry(T, B, &S, &seg_len)) {
+        SplitScratch* sc = nullptr;
+        rc = split_scratch(static_cast<size_t>(S) * static_cast<size_t>(B), stream, &sc);
+        if (rc) return rc;
+        const dim3 grid(static_cast<unsigned>((B + kSplitThreads - 1) / kSplitThreads), static_cast<unsigned>(S));
+        gae_bwd_split<false><<<grid, kSplitThreads, 0, stream>>>(grad_adv, ldg, dtab, sc->buf, gv, ldgv, gr, ldgr,
+                                                                 static_cast<int>(T), static_cast<int>(B), seg_len, g, f);
+        gae_bwd_split<true><<<grid, kSplitThreads, 0, stream>>>(grad_adv, ldg, dtab, sc->buf, gv, ldgv, gr, ldgr,
+                                                                static_cast<int>(T), static_cast<int>(B), seg_len, g, f);
+        count_launch(2);
+        HPC_LAUNCH_CHECK();
+        if (!stream_capturing(stream)) HPC_CUDA(cudaEventRecord(sc->done, stream));
+        return HPC_RLL_OK;
+    }
     int cfg = pick_cfg(B);
     if (!tma_ok_2d(grad_adv, B, ldg)) cfg = 99;
     switch (cfg) {

@@ -1,9 +1,10 @@
 """GAE parity on the GPU: CUDA kernels (through libhpc_rll_b200.so) vs the oracle / golden fixtures.
 
 Tolerances: forward and backward are element-wise chains evaluated in the oracle's exact fp32
-operation order, so both must be BIT-EXACT against oracle_f32 (and the forward against origin's
-own fp32 output in the golden fixtures).  Gradients vs origin autograd (different summation
-structure): 1e-5 norm-relative (north_star tolerance)."""
+operation order, so the column-scan kernels must be BIT-EXACT against oracle_f32 (and the forward
+against origin's own fp32 output in the golden fixtures).  The T-split kernels used for small batches
+(B <= 2048 and T >= 128) re-associate the recurrence across segments: 2e-6 norm-relative there.
+Gradients vs origin autograd (different summation structure): 1e-5 norm-relative (north_star)."""
 import numpy as np
 import pytest
 import torch
@@ -15,7 +16,18 @@ from tests._gpu import dev, host, need_cuda, rng
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1024, 64), (128, 128), (1, 5), (37, 3), (100, 260), (17, 1028), (64, 1), (33, 4), (250, 4096),
-          (16, 128), (15, 132)]
+          (16, 128), (15, 132), (1000, 7), (129, 2048), (513, 100), (2048, 36)]
+
+
+def uses_split(T, B):
+    return B <= 2048 and T >= 128
+
+
+def same(got, want, exact):
+    if exact:
+        assert np.array_equal(got, want)
+    else:
+        assert rel_err(got, want) <= 2e-6, rel_err(got, want)
 
 
 def _run(value, reward, grad_adv, gamma, lam):
@@ -36,10 +48,21 @@ def test_gae_vs_oracle_bitexact(T, B):
     reward = g.standard_normal((T, B), dtype=np.float32)
     gadv = g.standard_normal((T, B), dtype=np.float32)
     adv, gv, gr = _run(value, reward, gadv, 0.99, 0.97)
-    assert np.array_equal(adv, orc.gae_forward(value, reward, 0.99, 0.97))
+    exact = not uses_split(T, B)
     ob = orc.gae_backward(gadv, 0.99, 0.97)
-    assert np.array_equal(gv, ob["value"])
-    assert np.array_equal(gr, ob["reward"])
+    same(adv, orc.gae_forward(value, reward, 0.99, 0.97), exact)
+    same(gv, ob["value"], exact)
+    same(gr, ob["reward"], exact)
+    if not exact:  # the same shape through the column-scan kernel is bit-exact
+        from di_hpc_b200 import _abi
+        try:
+            _abi.set_config(0, 2)
+            adv, gv, gr = _run(value, reward, gadv, 0.99, 0.97)
+        finally:
+            _abi.set_config(0, -1)
+        same(adv, orc.gae_forward(value, reward, 0.99, 0.97), True)
+        same(gv, ob["value"], True)
+        same(gr, ob["reward"], True)
 
 
 @pytest.mark.parametrize("name", names("gae"))
@@ -47,16 +70,17 @@ def test_gae_vs_golden(name):
     need_cuda()
     c = Case(name)
     adv, gv, gr = _run(c.inp("value"), c.inp("reward"), c.inp("grad_adv"), c.attr("gamma"), c.attr("lambda_"))
-    assert np.array_equal(adv, c.out("adv", 32)), "forward must be bit-exact vs origin fp32"
+    T, B = c.inp("reward").shape
+    same(adv, c.out("adv", 32), not uses_split(T, B))  # bit-exact vs origin fp32 on the column-scan path
     assert rel_err(gv, c.grad("value", 32)) <= 1e-5
     assert rel_err(gr, c.grad("reward", 32)) <= 1e-5
     assert rel_err(gv, c.grad("value", 64)) <= 1e-5
     assert rel_err(gr, c.grad("reward", 64)) <= 1e-5
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 13, 14, 99])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 13, 14, 20, 99])
 def test_gae_every_kernel_config(cfg):
-    """All tile configurations (and the non-TMA kernel) must give identical bits."""
+    """All tile configurations (and the non-TMA kernel) must give identical bits; 20 = T-split."""
     need_cuda()
     from di_hpc_b200 import _abi
     g = rng(77 + cfg)
@@ -69,9 +93,10 @@ def test_gae_every_kernel_config(cfg):
         adv, gv, gr = _run(value, reward, gadv, 0.95, 0.9)
     finally:
         _abi.set_config(0, -1)
-    assert np.array_equal(adv, orc.gae_forward(value, reward, 0.95, 0.9))
     ob = orc.gae_backward(gadv, 0.95, 0.9)
-    assert np.array_equal(gv, ob["value"]) and np.array_equal(gr, ob["reward"])
+    same(adv, orc.gae_forward(value, reward, 0.95, 0.9), cfg != 20)
+    same(gv, ob["value"], cfg != 20)
+    same(gr, ob["reward"], cfg != 20)
 
 
 def test_gae_strided_views():
@@ -131,9 +156,11 @@ def test_gae_host_entry_matches_device_path():
     _abi.check(_abi.lib().hpc_rll_gae_fwd_bwd_host(value.data_ptr(), reward.data_ptr(), gadv.data_ptr(),
                                                    adv.data_ptr(), gv.data_ptr(), gr.data_ptr(), T, B, 0.99, 0.97),
                "gae_fwd_bwd_host")
-    assert np.array_equal(adv.numpy(), orc.gae_forward(value.numpy(), reward.numpy()))
+    # the last (narrow) column block may take the T-split path: tolerance instead of bit equality
     ob = orc.gae_backward(gadv.numpy())
-    assert np.array_equal(gv.numpy(), ob["value"]) and np.array_equal(gr.numpy(), ob["reward"])
+    same(adv.numpy(), orc.gae_forward(value.numpy(), reward.numpy()), False)
+    same(gv.numpy(), ob["value"], False)
+    same(gr.numpy(), ob["reward"], False)
 
 
 def test_gae_argument_errors():
