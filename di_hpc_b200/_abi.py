@@ -92,6 +92,25 @@ def stream_of(t) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOGUARD = _NoGuard()
+
+
+def on_device(device):
+    """Device guard for the C-ABI calls (they act on the CURRENT device).  Free when the tensor already
+    lives on the current device -- the common one-process-per-GPU case."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NOGUARD
+    return torch.cuda.device(device)
+
+
 def require_f32_cuda(name: str, t: torch.Tensor) -> torch.Tensor:
     """The reference assumes fp32 contiguous CUDA tensors (hpc_rll/rl_utils/gae.py:58-59 asserts
     is_cuda only); we check dtype and make the layout contiguous."""

@@ -23,7 +23,7 @@ class GAEFunction(torch.autograd.Function):
         if value.shape != (T + 1, B):
             raise ValueError("value must be (T+1, B)=(%d, %d), got %s" % (T + 1, B, tuple(value.shape)))
         adv = torch.empty_like(reward)
-        with torch.cuda.device(reward.device):
+        with _abi.on_device(reward.device):
             _abi.check(
                 _abi.lib().hpc_rll_gae_forward(_abi.ptr(value), _abi.ptr(reward), _abi.ptr(adv), T, B, float(gamma),
                                                float(lambda_), _abi.stream_of(reward)), "hpc_rll_gae_forward")
@@ -36,7 +36,7 @@ class GAEFunction(torch.autograd.Function):
         grad_adv = _abi.require_f32_cuda("grad_adv", grad_adv)
         grad_value = torch.empty((T + 1, B), dtype=torch.float32, device=grad_adv.device)
         grad_reward = torch.empty((T, B), dtype=torch.float32, device=grad_adv.device)
-        with torch.cuda.device(grad_adv.device):
+        with _abi.on_device(grad_adv.device):
             _abi.check(
                 _abi.lib().hpc_rll_gae_backward(_abi.ptr(grad_adv), _abi.ptr(grad_value), _abi.ptr(grad_reward), T, B,
                                                 ctx.gamma, ctx.lambda_, _abi.stream_of(grad_adv)),

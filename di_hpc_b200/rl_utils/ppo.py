@@ -37,7 +37,7 @@ class PPOFunction(torch.autograd.Function):
         pol_coef = torch.empty(B, dtype=torch.float32, device=dev)
         val_coef = torch.empty(B, dtype=torch.float32, device=dev)
         ws = _abi.workspace(_abi.OP_PPO, 0, B, N, dev)
-        with torch.cuda.device(dev):
+        with _abi.on_device(dev):
             _abi.check(
                 _abi.lib().hpc_rll_ppo_forward(_abi.ptr(logits_new), _abi.ptr(logits_old), _abi.ptr(action),
                                                _abi.ptr(value_new), _abi.ptr(value_old), _abi.ptr(adv),
@@ -61,7 +61,7 @@ class PPOFunction(torch.autograd.Function):
         g_e = _abi.grad_scalar(grad_entropy_loss, pol_coef)
         grad_logits = torch.empty_like(logits_new)
         grad_value = torch.empty(B, dtype=torch.float32, device=pol_coef.device)
-        with torch.cuda.device(pol_coef.device):
+        with _abi.on_device(pol_coef.device):
             _abi.check(
                 _abi.lib().hpc_rll_ppo_backward(_abi.ptr(g_p), _abi.ptr(g_v), _abi.ptr(g_e), _abi.ptr(logits_new),
                                                 _abi.ptr(action), _abi.ptr(weight), _abi.ptr(pol_coef),

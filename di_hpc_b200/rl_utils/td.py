@@ -60,7 +60,7 @@ class TDLambdaFunction(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=reward.device)
         grad_buf = torch.empty_like(reward)
         ws = _abi.workspace(_abi.OP_TD_LAMBDA, T, B, 0, reward.device)
-        with torch.cuda.device(reward.device):
+        with _abi.on_device(reward.device):
             _abi.check(
                 _abi.lib().hpc_rll_td_lambda_forward(_abi.ptr(value), _abi.ptr(reward), _abi.ptr(weight),
                                                      _abi.ptr(loss), _abi.ptr(grad_buf), T, B, float(gamma),
@@ -75,7 +75,7 @@ class TDLambdaFunction(torch.autograd.Function):
         T, B = grad_buf.shape
         g = _abi.grad_scalar(grad_loss, grad_buf)
         grad_value = torch.empty((T + 1, B), dtype=torch.float32, device=grad_buf.device)
-        with torch.cuda.device(grad_buf.device):
+        with _abi.on_device(grad_buf.device):
             _abi.check(
                 _abi.lib().hpc_rll_td_lambda_backward(_abi.ptr(g), _abi.ptr(grad_buf), _abi.ptr(grad_value), T, B,
                                                       _abi.stream_of(grad_buf)), "hpc_rll_td_lambda_backward")
@@ -137,7 +137,7 @@ class _QNStepTDBase(torch.autograd.Function):
         td_err = torch.empty(B, dtype=torch.float32, device=dev)
         grad_buf = torch.empty(B, dtype=torch.float32, device=dev)
         ws = _abi.workspace(_abi.OP_Q_NSTEP_TD, T, B, N, dev)
-        with torch.cuda.device(dev):
+        with _abi.on_device(dev):
             _abi.check(
                 _abi.lib().hpc_rll_q_nstep_td_forward(_abi.ptr(q), _abi.ptr(next_n_q), _abi.ptr(action),
                                                       _abi.ptr(next_n_action), _abi.ptr(reward), _abi.ptr(done),
@@ -156,7 +156,7 @@ class _QNStepTDBase(torch.autograd.Function):
         B, N = grad_buf.shape[0], ctx.N
         g = _abi.grad_scalar(grad_loss, grad_buf)
         grad_q = torch.empty((B, N), dtype=torch.float32, device=grad_buf.device)
-        with torch.cuda.device(grad_buf.device):
+        with _abi.on_device(grad_buf.device):
             _abi.check(
                 _abi.lib().hpc_rll_q_nstep_td_backward(_abi.ptr(g), _abi.ptr(grad_buf), _abi.ptr(action),
                                                        _abi.ptr(grad_q), B, N, _abi.stream_of(grad_buf)),
@@ -257,7 +257,7 @@ class DistNStepTDFunction(torch.autograd.Function):
         td_err = torch.empty(B, dtype=torch.float32, device=dev)
         grad_buf = torch.empty((B, n_atom), dtype=torch.float32, device=dev)
         ws = _abi.workspace(_abi.OP_DIST_NSTEP_TD, T, B, N, dev)
-        with torch.cuda.device(dev):
+        with _abi.on_device(dev):
             _abi.check(
                 _abi.lib().hpc_rll_dist_nstep_td_forward(_abi.ptr(dist), _abi.ptr(next_n_dist), _abi.ptr(action),
                                                          _abi.ptr(next_n_action), _abi.ptr(reward), _abi.ptr(done),
@@ -278,7 +278,7 @@ class DistNStepTDFunction(torch.autograd.Function):
         N = ctx.N
         g = _abi.grad_scalar(grad_loss, grad_buf)
         grad_dist = torch.empty((B, N, n_atom), dtype=torch.float32, device=grad_buf.device)
-        with torch.cuda.device(grad_buf.device):
+        with _abi.on_device(grad_buf.device):
             _abi.check(
                 _abi.lib().hpc_rll_dist_nstep_td_backward(_abi.ptr(g), _abi.ptr(grad_buf), _abi.ptr(action),
                                                           _abi.ptr(grad_dist), B, N, n_atom,
@@ -356,7 +356,7 @@ class QRDQNNStepTDErrorFunction(torch.autograd.Function):
         td_err = torch.empty(B, dtype=torch.float32, device=dev)
         grad_buf = torch.empty((B, tau), dtype=torch.float32, device=dev)
         ws = _abi.workspace(_abi.OP_QRDQN_NSTEP_TD, T, B, N, dev)
-        with torch.cuda.device(dev):
+        with _abi.on_device(dev):
             _abi.check(
                 _abi.lib().hpc_rll_qrdqn_nstep_td_forward(_abi.ptr(q), _abi.ptr(next_n_q), _abi.ptr(action),
                                                           _abi.ptr(next_n_action), _abi.ptr(reward), _abi.ptr(done),
@@ -376,7 +376,7 @@ class QRDQNNStepTDErrorFunction(torch.autograd.Function):
         N = ctx.N
         g = _abi.grad_scalar(grad_loss, grad_buf)
         grad_q = torch.empty((B, N, tau), dtype=torch.float32, device=grad_buf.device)
-        with torch.cuda.device(grad_buf.device):
+        with _abi.on_device(grad_buf.device):
             _abi.check(
                 _abi.lib().hpc_rll_qrdqn_nstep_td_backward(_abi.ptr(g), _abi.ptr(grad_buf), _abi.ptr(action),
                                                            _abi.ptr(grad_q), tau, B, N, _abi.stream_of(grad_buf)),
@@ -456,7 +456,7 @@ class IQNNStepTDErrorFunction(torch.autograd.Function):
         td_err = torch.empty(B, dtype=torch.float32, device=dev)
         grad_buf = torch.empty((tau, B), dtype=torch.float32, device=dev)
         ws = _abi.workspace(_abi.OP_IQN_NSTEP_TD, T, B, N, dev)
-        with torch.cuda.device(dev):
+        with _abi.on_device(dev):
             _abi.check(
                 _abi.lib().hpc_rll_iqn_nstep_td_forward(_abi.ptr(q), _abi.ptr(next_n_q), _abi.ptr(action),
                                                         _abi.ptr(next_n_action), _abi.ptr(reward), _abi.ptr(done),
@@ -477,7 +477,7 @@ class IQNNStepTDErrorFunction(torch.autograd.Function):
         N = ctx.N
         g = _abi.grad_scalar(grad_loss, grad_buf)
         grad_q = torch.empty((tau, B, N), dtype=torch.float32, device=grad_buf.device)
-        with torch.cuda.device(grad_buf.device):
+        with _abi.on_device(grad_buf.device):
             _abi.check(
                 _abi.lib().hpc_rll_iqn_nstep_td_backward(_abi.ptr(g), _abi.ptr(grad_buf), _abi.ptr(action),
                                                          _abi.ptr(grad_q), tau, B, N, _abi.stream_of(grad_buf)),

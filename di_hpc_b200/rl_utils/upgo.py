@@ -22,7 +22,7 @@ class UpgoFunction(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         coef = torch.empty((T, B), dtype=torch.float32, device=dev)
         ws = _abi.workspace(_abi.OP_UPGO, T, B, N, dev)
-        with torch.cuda.device(dev):
+        with _abi.on_device(dev):
             _abi.check(
                 _abi.lib().hpc_rll_upgo_forward(_abi.ptr(target_output), _abi.ptr(rho), _abi.ptr(action),
                                                 _abi.ptr(reward), _abi.ptr(value), _abi.ptr(loss), _abi.ptr(coef), T,
@@ -37,7 +37,7 @@ class UpgoFunction(torch.autograd.Function):
         T, B, N = target_output.shape
         g = _abi.grad_scalar(grad_loss, coef)
         grad_target = torch.empty_like(target_output)
-        with torch.cuda.device(coef.device):
+        with _abi.on_device(coef.device):
             _abi.check(
                 _abi.lib().hpc_rll_upgo_backward(_abi.ptr(g), _abi.ptr(target_output), _abi.ptr(action),
                                                  _abi.ptr(coef), _abi.ptr(grad_target), T, B, N,

@@ -33,7 +33,7 @@ class VtraceFunction(torch.autograd.Function):
         pg_coef = torch.empty((T, B), dtype=torch.float32, device=dev)
         gv_buf = torch.empty((T, B), dtype=torch.float32, device=dev)
         ws = _abi.workspace(_abi.OP_VTRACE, T, B, N, dev)
-        with torch.cuda.device(dev):
+        with _abi.on_device(dev):
             _abi.check(
                 _abi.lib().hpc_rll_vtrace_forward(
                     _abi.ptr(target_output), _abi.ptr(behaviour_output), _abi.ptr(action), _abi.ptr(value),
@@ -54,7 +54,7 @@ class VtraceFunction(torch.autograd.Function):
         g_e = _abi.grad_scalar(grad_entropy_loss, pg_coef)
         grad_target = torch.empty_like(target_output)
         grad_value = torch.empty((T + 1, B), dtype=torch.float32, device=pg_coef.device)
-        with torch.cuda.device(pg_coef.device):
+        with _abi.on_device(pg_coef.device):
             _abi.check(
                 _abi.lib().hpc_rll_vtrace_backward(_abi.ptr(g_pg), _abi.ptr(g_v), _abi.ptr(g_e),
                                                    _abi.ptr(target_output), _abi.ptr(action), _abi.ptr(weight),
