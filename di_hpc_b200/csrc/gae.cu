@@ -450,7 +450,7 @@ static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab,
 //   3: BT=64  TT=32 ST=3      4: BT=128 TT=8  ST=4     5: BT=64 TT=8  ST=6
 //   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     8: BT=256 TT=16 ST=3
 //  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     13: BT=32 TT=64 ST=6   14: BT=32 TT=16 ST=12
-//  20: T-split (small batch; automatic for B <= 1024 and T >= 512)   99: generic (non-TMA) kernel
+//  20: T-split (small batch; opt-in)   99: generic (non-TMA) kernel
 // (a TMA box dimension is limited to 256 elements, so BT <= 256)
 static int pick_cfg(int64_t B) {
     const int forced = tuning_config(HPC_RLL_OP_GAE);
@@ -459,16 +459,18 @@ static int pick_cfg(int64_t B) {
     if (B >= 256 * sms) return 7;
     if (B >= 128 * sms) return 1;
     if (B >= 64 * sms) return 0;
-    return 2;
+    if (B >= 32 * sms) return 2;
+    return 13;  // few column tiles: deeper row pipeline per CTA
 }
 
 // T-split geometry: S segments of seg_len rows so that tiles*S covers the machine about twice
 static bool split_geometry(int64_t T, int64_t B, int* S, int* seg_len) {
     const int forced = tuning_config(HPC_RLL_OP_GAE);
     if (forced >= 0 && forced != 20) return false;
-    // measured on B200 (profiles/r01_gae_small_batch.md): pays off for long, narrow problems only; everything
-    // smaller is launch-latency bound either way
-    if (forced < 0 && !(B <= 1024 && T >= 512)) return false;
+    // opt-in (config 20): measured on B200 (profiles/r01_gae_small_batch.md) the two launches halve the device
+    // time of long narrow problems (T=1024, B=64: 64 -> 41 us) but eager PyTorch calls are CPU-launch bound
+    // there, so it only pays under CUDA-graph replay
+    if (forced < 0) return false;
     const int64_t tiles = (B + kSplitThreads - 1) / kSplitThreads;
     int64_t s = (2 * static_cast<int64_t>(sm_count()) + tiles - 1) / tiles;
     if (s > 32) s = 32;
