@@ -452,8 +452,10 @@ static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab,
 //  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     13: BT=32 TT=64 ST=6   14: BT=32 TT=16 ST=12
 //  20: T-split (small batch; opt-in)   99: generic (non-TMA) kernel
 // (a TMA box dimension is limited to 256 elements, so BT <= 256)
-static int pick_cfg(int64_t B) {
-    const int forced = tuning_config(HPC_RLL_OP_GAE);
+// forced values >= 100 encode different kernels per direction: forward = v % 100, backward = v / 100
+static int pick_cfg(int64_t B, bool backward = false) {
+    int forced = tuning_config(HPC_RLL_OP_GAE);
+    if (forced >= 100) forced = backward ? forced / 100 : forced % 100;
     if (forced >= 0) return forced;
     const int64_t sms = sm_count();
     if (B >= 256 * sms) return 7;
@@ -608,7 +610,7 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
         if (!stream_capturing(stream)) HPC_CUDA(cudaEventRecord(sc->done, stream));
         return HPC_RLL_OK;
     }
-    int cfg = pick_cfg(B);
+    int cfg = pick_cfg(B, true);
     if (!tma_ok_2d(grad_adv, B, ldg)) cfg = 99;
     switch (cfg) {
         case 0: return launch_bwd_tma<64, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
