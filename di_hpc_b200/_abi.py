@@ -47,6 +47,10 @@ SIGNATURES = {
     "hpc_rll_qrdqn_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 3 + [c_vp]),
     "hpc_rll_iqn_nstep_td_forward": (c_int, [c_vp] * 12 + [c_i64] * 5 + [c_dbl, c_dbl, c_i64, c_vp, c_sz, c_vp]),
     "hpc_rll_iqn_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 3 + [c_vp]),
+    "hpc_rll_pad_batch": (c_int, [c_vp] * 5 + [c_i64, c_int, c_vp]),
+    "hpc_rll_unpad_batch": (c_int, [c_vp] * 4 + [c_i64, c_vp]),
+    "hpc_rll_oracle_split_group": (c_int, [c_vp, c_i64, c_int, c_int, c_vp]),
+    "hpc_rll_sample_split_group": (c_int, [c_vp, c_i64, c_int, c_int, ctypes.c_uint64, c_vp, c_vp]),
 }
 
 OP_GAE, OP_TD_LAMBDA, OP_VTRACE, OP_UPGO, OP_PPO, OP_Q_NSTEP_TD, OP_DIST_NSTEP_TD, OP_QRDQN_NSTEP_TD, \

@@ -198,6 +198,26 @@ int hpc_rll_iqn_nstep_td_forward(const float* q, const float* next_n_q, const in
 int hpc_rll_iqn_nstep_td_backward(const float* grad_loss, const float* grad_buf, const int64_t* action,
                                   float* grad_q, int64_t tau, int64_t B, int64_t N, void* stream);
 
+/* ---- ragged-tensor padding (the data format on the input side of the path) -----------------------
+ * replaces Pad{1,2,3}DForward / GroupPad{1,2,3}DForward / Unpad{1,2,3}DForward and the two group splitters
+ * (/root/reference/src/rl_utils/padding.cu:8-589, kernels include/hpc/rll/cuda/rl_utils/padding_kernel.h:100-233);
+ * semantics of hpc_rll/origin/padding.py.  Descriptor tables are HOST arrays of length n (device pointers
+ * inside); shapes / padded are n x 3 int32 (trailing dims 1 for 1-D / 2-D).  No allocation, no copy: the
+ * tables ride in kernel parameter space.
+ *   pad  : dst[k] (padded slot, prod(padded[k]) floats) = src[k] inside shapes[k], `value` elsewhere;
+ *          mask[k] (int32) = 1 inside, `value` elsewhere
+ *   unpad: dst[k] (prod(shapes[k]) floats) = the leading shapes[k] block of the padded slot src[k] */
+int hpc_rll_pad_batch(const float* const* src, float* const* dst, int32_t* const* mask, const int32_t* shapes,
+                      const int32_t* padded, int64_t n, int value, void* stream);
+int hpc_rll_unpad_batch(const float* const* src, float* const* dst, const int32_t* shapes, const int32_t* padded,
+                        int64_t n, void* stream);
+/* host-only helpers: split a size-sorted shape list (n x ndim int64) into groups.
+ * oracle: exactly `group` groups minimising the padded volume; positions[0..group], positions[group] = n.
+ * sample: random boundaries (deterministic per seed), equal-shaped neighbours merged; starts[0..*n_groups]. */
+int hpc_rll_oracle_split_group(const int64_t* shapes, int64_t n, int ndim, int group, int64_t* positions);
+int hpc_rll_sample_split_group(const int64_t* shapes, int64_t n, int ndim, int group, uint64_t seed,
+                               int64_t* starts, int* n_groups);
+
 #ifdef __cplusplus
 }
 #endif

@@ -258,6 +258,31 @@ def case_iqn(name, tau, tau_p, T, B, N, gamma, kappa, use_weight, use_vg, seed):
     save_case(name, fn, inputs, ["q"], dict(gamma=gamma, kappa=kappa, coef_loss=0.8))
 
 
+# ----------------------------------------------------------------------------- padding
+def case_padding(name, ndim, n, lo_hi, value, group, seed):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_origin_padding",
+                                                  os.path.join(_ref_origin.REF_ROOT, "hpc_rll", "origin", "padding.py"))
+    P = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(P)
+    rng = np.random.default_rng(seed)
+    shapes = [tuple(int(rng.integers(lo, hi)) for lo, hi in lo_hi) for _ in range(n)]
+    g = gen(seed)
+    data = [torch.randn(*s, generator=g) for s in shapes]
+    pad = {1: P.Padding1D, 2: P.Padding2D, 3: P.Padding3D}[ndim]
+    new_x, mask, ori_shapes = pad(data, value=value)
+    blob = {"n": np.asarray(n), "ndim": np.asarray(ndim), "value": np.asarray(value), "group": np.asarray(group),
+            "shapes": np.asarray(shapes, dtype=np.int64), "new_x": _np(new_x), "mask": _np(mask)}
+    for i, d in enumerate(data):
+        blob["x%d" % i] = _np(d)
+    sorted_shapes = sorted(shapes, key=lambda t: int(np.prod(t)))
+    sorted_data = sorted(data, key=lambda t: int(np.prod(t.shape)))
+    _, positions = P.oracle_split_group(sorted_data, group)
+    blob["sorted_shapes"] = np.asarray(sorted_shapes, dtype=np.int64)
+    blob["positions"] = np.asarray(positions, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
+
+
 def main():
     for f in os.listdir(HERE):
         if f.endswith(".npz"):
@@ -311,6 +336,11 @@ def main():
     case_iqn("iqn_tau33_34_t10_b5_n3_w_vg", 33, 34, 10, 5, 3, 0.95, 0.9, True, True, s + 81)
     case_iqn("iqn_tau64_64_t5_b3_n2_w", 64, 64, 5, 3, 2, 0.99, 1.0, True, False, s + 82)
     case_iqn("iqn_tau1_1_t1_b4_n1", 1, 1, 1, 4, 1, 0.9, 0.5, False, False, s + 83)
+    case_padding("padding_1d_n64", 1, 64, [(32, 128)], 0, 4, s + 90)       # tests/test_padding.py:10-11
+    case_padding("padding_1d_n7_v3", 1, 7, [(1, 9)], 3, 3, s + 91)
+    case_padding("padding_2d_n12", 2, 12, [(6, 14), (4, 11)], 0, 4, s + 92)   # (test_padding.py:12 ranges, scaled down)
+    case_padding("padding_3d_n8", 3, 8, [(3, 7), (3, 6), (4, 9)], 0, 3, s + 93)  # (test_padding.py:13, scaled down)
+    case_padding("padding_3d_n5_small", 3, 5, [(1, 4), (1, 5), (1, 6)], -1, 2, s + 94)
     n = len([f for f in os.listdir(HERE) if f.endswith(".npz")])
     tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print("wrote %d fixtures, %.1f KB" % (n, tot / 1024))
