@@ -70,16 +70,18 @@ static int pad_batch(const float* const* src, float* const* dst, int32_t* const*
             p.src = src[k];
             p.dst = dst[k];
             p.mask = unpad ? nullptr : mask[k];
-            int64_t tot = 1;
+            int64_t tot = 1, own = 1;
             for (int d = 0; d < 3; ++d) {
                 p.s[d] = shapes[k * 3 + d];
                 p.m[d] = padded[k * 3 + d];
                 HPC_REQUIRE(p.s[d] >= 0 && p.m[d] >= p.s[d], "pad: item %lld dim %d: shape %d exceeds padded %d",
                             (long long)k, d, p.s[d], p.m[d]);
                 tot *= unpad ? p.s[d] : p.m[d];
+                own *= p.s[d];
             }
-            HPC_REQUIRE(tot == 0 || (p.src && p.dst && (unpad || p.mask)), "pad: null tensor pointer at item %lld",
-                        (long long)k);
+            // an empty source tensor has no storage (null pointer) and is never dereferenced
+            HPC_REQUIRE((own == 0 || p.src) && (tot == 0 || (p.dst && (unpad || p.mask))),
+                        "pad: null tensor pointer at item %lld", (long long)k);
             max_total = std::max(max_total, tot);
         }
         int64_t by = (max_total + 256 * 4 - 1) / (256 * 4);

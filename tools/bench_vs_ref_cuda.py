@@ -189,6 +189,36 @@ def qrdqn_case(R, tau, T, B, N):
                 err=max(relerr(loss, loss_r), relerr(td, td_r), relerr(gq, gq_r)))
 
 
+def padding_case(R, ndim, B, ranges, seed=0):
+    """pad + unpad of B ragged tensors (reference: Pad{n}DForward / Unpad{n}DForward pybind calls; ours: the
+    drop-in Python functions, i.e. including our Python-side table building)."""
+    import numpy as np
+    import hpc_rll.rl_utils.padding as H
+    rng = np.random.default_rng(seed)
+    shapes = [tuple(int(rng.integers(lo, hi)) for lo, hi in ranges) for _ in range(B)]
+    data = [torch.randn(*s, device=DEV) for s in shapes]
+    flat = [int(v) for s in shapes for v in s]
+    rpad = {1: R.Pad1DForward, 2: R.Pad2DForward, 3: R.Pad3DForward}[ndim]
+    runpad = {1: R.Unpad1DForward, 2: R.Unpad2DForward, 3: R.Unpad3DForward}[ndim]
+    opad = {1: H.Padding1D, 2: H.Padding2D, 3: H.Padding3D}[ndim]
+    ounpad = {1: H.UnPadding1D, 2: H.UnPadding2D, 3: H.UnPadding3D}[ndim]
+    keep = {}
+
+    def ref():
+        x, m = rpad(data, 0)
+        keep["r"] = (x, runpad(x, flat))
+
+    def ours():
+        x, m, shp = opad(data)
+        keep["o"] = (x, ounpad(x, shp))
+
+    tr, to = med_ms(ref, 20), med_ms(ours, 20)
+    err = relerr(keep["o"][0], keep["r"][0])
+    for a, b in zip(keep["o"][1], keep["r"][1]):
+        err = max(err, relerr(a, b))
+    return dict(op="pad+unpad %dD" % ndim, shape="B=%d ranges=%s" % (B, ranges), ref_ms=tr, ours_ms=to, err=err)
+
+
 def main():
     R = load_ref()
     if R is None:
@@ -205,6 +235,10 @@ def main():
         lambda: upgo_case(R, 512, 32768, 16),   # BASELINE C2
         lambda: qrdqn_case(R, 39, 10, 89, 67),  # tests/test_qrdqn_nstep_td_error.py:10-14
         lambda: qrdqn_case(R, 64, 5, 65535, 8), # largest batch the reference can launch (grid.y = B)
+        lambda: padding_case(R, 1, 64, [(32, 128)]),                        # tests/test_padding.py:9-11
+        lambda: padding_case(R, 2, 64, [(48, 80), (32, 64)]),               # tests/test_padding.py:12
+        lambda: padding_case(R, 3, 64, [(24, 32), (24, 32), (32, 40)]),     # tests/test_padding.py:13
+        lambda: padding_case(R, 2, 256, [(400, 512), (400, 512)]),          # large: 256 x ~200k elements
     ]
     rows = []
     for fn in plan:
