@@ -25,32 +25,40 @@ struct PadItem {
     const float* src;
     float* dst;
     int32_t* mask;  // pad only
-    int s[3];       // own shape (trailing dims 1 for lower rank)
-    int m[3];       // padded shape of its group
+    int s[3];       // own shape, right-aligned (leading dims 1 for lower rank)
+    int m[3];       // padded shape of its group, right-aligned
 };
 constexpr int kPadChunk = 512;
 struct PadBatch {
     PadItem it[kPadChunk];
 };
 
+// Shapes are right-aligned into 3 dims (1-D: (1,1,L); 2-D: (1,A,B)), so an item is a list of ROWS of
+// d2 contiguous elements.  One warp per row at a time, lanes along the row: no per-element division,
+// coalesced reads and writes; rows are spread over the 8 warps of a CTA and over gridDim.y CTAs.
 template <bool UNPAD>
 __global__ void __launch_bounds__(256) pad_kernel(const __grid_constant__ PadBatch batch, float value, int ivalue) {
     const PadItem& p = batch.it[blockIdx.x];
-    const int s1 = p.s[1], s2 = p.s[2], m1 = p.m[1], m2 = p.m[2];
-    const int64_t total = UNPAD ? static_cast<int64_t>(p.s[0]) * s1 * s2 : static_cast<int64_t>(p.m[0]) * m1 * m2;
-    const int d1 = UNPAD ? s1 : m1, d2 = UNPAD ? s2 : m2;
-    for (int64_t e = static_cast<int64_t>(blockIdx.y) * blockDim.x + threadIdx.x; e < total;
-         e += static_cast<int64_t>(gridDim.y) * blockDim.x) {
-        const int c = static_cast<int>(e % d2);
-        const int64_t ab = e / d2;
-        const int b = static_cast<int>(ab % d1);
-        const int a = static_cast<int>(ab / d1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s0 = p.s[0], s1 = p.s[1], s2 = p.s[2], m1 = p.m[1], m2 = p.m[2];
+    const int d0 = UNPAD ? s0 : p.m[0], d1 = UNPAD ? s1 : m1, d2 = UNPAD ? s2 : m2;
+    const int64_t rows = static_cast<int64_t>(d0) * d1;
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + warp; r < rows; r += static_cast<int64_t>(gridDim.y) * 8) {
+        const int a = static_cast<int>(r / d1), b = static_cast<int>(r - static_cast<int64_t>(a) * d1);
         if (UNPAD) {
-            p.dst[e] = __ldg(p.src + (static_cast<int64_t>(a) * m1 + b) * m2 + c);
+            const float* __restrict__ src = p.src + (static_cast<int64_t>(a) * m1 + b) * m2;
+            float* __restrict__ dst = p.dst + r * s2;
+            for (int c = lane; c < s2; c += 32) dst[c] = __ldg(src + c);
         } else {
-            const bool inside = a < p.s[0] && b < s1 && c < s2;
-            p.dst[e] = inside ? __ldg(p.src + (static_cast<int64_t>(a) * s1 + b) * s2 + c) : value;
-            p.mask[e] = inside ? 1 : ivalue;
+            const bool row_in = a < s0 && b < s1;
+            const float* __restrict__ src = p.src + (static_cast<int64_t>(a) * s1 + b) * s2;
+            float* __restrict__ dst = p.dst + r * m2;
+            int32_t* __restrict__ msk = p.mask + r * m2;
+            for (int c = lane; c < m2; c += 32) {
+                const bool inside = row_in && c < s2;
+                dst[c] = inside ? __ldg(src + c) : value;
+                msk[c] = inside ? 1 : ivalue;
+            }
         }
     }
 }
@@ -84,8 +92,9 @@ static int pad_batch(const float* const* src, float* const* dst, int32_t* const*
                         "pad: null tensor pointer at item %lld", (long long)k);
             max_total = std::max(max_total, tot);
         }
-        int64_t by = (max_total + 256 * 4 - 1) / (256 * 4);
-        by = std::min<int64_t>(std::max<int64_t>(by, 1), 1024);
+        // ~2048 elements per CTA pass; enough CTAs per item to spread big tensors over the machine
+        int64_t by = (max_total + 2047) / 2048;
+        by = std::min<int64_t>(std::max<int64_t>(by, 1), 2048);
         const dim3 grid(static_cast<unsigned>(cnt), static_cast<unsigned>(by));
         if (unpad)
             pad_kernel<true><<<grid, 256, 0, stream>>>(batch, static_cast<float>(value), value);

@@ -6,7 +6,8 @@ reference's CUDA path returns it.
 
 One CUDA launch pads every tensor of every group: the per-tensor descriptors travel in kernel parameter
 space (di_hpc_b200/csrc/padding.cu), so a call performs no cudaMalloc / cudaMemcpy (the reference does up
-to 7 of each per call, src/rl_utils/padding.cu:118-131,172-199).
+to 7 of each per call, src/rl_utils/padding.cu:118-131,172-199).  UnPadding writes all outputs into one
+allocation and returns views of it (origin's default ``deepcopy=False`` also returns views).
 """
 import ctypes
 import itertools
@@ -19,133 +20,182 @@ import torch
 from .. import _abi
 
 _seed = itertools.count(0x5EED)
+_F32 = torch.float32
+
+
+def _load_ext():
+    """The thin torch/pybind layer (di_hpc_b200/csrc_torch/ext.cpp) does the per-tensor host work in C++.
+    It is optional: without it the same CUDA kernels are driven through ctypes from Python (slower host
+    side, identical results)."""
+    import glob
+    import importlib.util
+    import os
+    from .._abi import LIB_PATH
+    cands = glob.glob(os.path.join(os.path.dirname(LIB_PATH), "hpc_rl_utils_b200*.so"))
+    if not cands:
+        return None
+    try:
+        spec = importlib.util.spec_from_file_location("hpc_rl_utils_b200", cands[0])
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    except Exception:  # e.g. built against another torch: the ctypes path still works
+        return None
+
+
+_ext = _load_ext()
 
 
 def cum(t) -> int:
-    return reduce(lambda x, y: x * y, t)
+    return reduce(lambda x, y: x * y, t, 1)
 
 
-def _check_inputs(inputs, ndim):
+def _prepare(inputs, ndim):
+    """Validate once, return (contiguous tensors, shapes as an (n, ndim) int64 array)."""
     assert len(inputs) > 0, "empty input list"
     dev = inputs[0].device
-    out = []
-    for t in inputs:
-        assert t.is_cuda, "hpc version only supports cuda"
-        if t.dtype != torch.float32:
-            raise TypeError("padding supports float32 tensors, got %s" % t.dtype)
-        if t.dim() != ndim:
-            raise ValueError("expected %d-D tensors, got shape %s" % (ndim, tuple(t.shape)))
-        if t.device != dev:
-            raise ValueError("all tensors must live on one device")
-        out.append(t.contiguous())
+    assert dev.type == "cuda", "hpc version only supports cuda"
+    shapes = [t.shape for t in inputs]
+    if any(len(s) != ndim for s in shapes):
+        raise ValueError("expected %d-D tensors" % ndim)
+    if any(t.dtype is not _F32 for t in inputs):
+        raise TypeError("padding supports float32 tensors")
+    if any(t.device != dev for t in inputs):
+        raise ValueError("all tensors must live on one CUDA device")
+    if not all(t.is_contiguous() for t in inputs):
+        inputs = [t.contiguous() for t in inputs]
+    return list(inputs), np.array(shapes, dtype=np.int64).reshape(len(inputs), ndim)
+
+
+def _right3(a):
+    """(n, ndim) -> (n, 3) int32, right-aligned with leading ones."""
+    n, nd = a.shape
+    out = np.ones((n, 3), dtype=np.int32)
+    out[:, 3 - nd:] = a
     return out
 
 
-def _table(ptrs):
-    return (ctypes.c_void_p * len(ptrs))(*ptrs)
+def _ptr_table(ptrs):
+    return np.array(ptrs, dtype=np.uint64)
 
 
-def _shape3(shapes):
-    a = np.ones((len(shapes), 3), dtype=np.int32)
-    for i, s in enumerate(shapes):
-        a[i, :len(s)] = s
-    return a
-
-
-def _pad_groups(inputs, ndim, bounds, value):
+def _pad_groups(inputs, shp, bounds, value):
     """Pad inputs[bounds[g]:bounds[g+1]] to the max shape of group g -- one launch for all groups."""
     dev = inputs[0].device
-    n = len(inputs)
-    shapes = [tuple(t.shape) for t in inputs]
-    new_x, masks, padded = [], [], []
-    dst, msk = [0] * n, [0] * n
+    n, ndim = shp.shape
+    new_x, masks = [], []
+    dst = np.empty(n, dtype=np.uint64)
+    msk = np.empty(n, dtype=np.uint64)
+    padded = np.empty((n, ndim), dtype=np.int64)
     for g in range(len(bounds) - 1):
         lo, hi = bounds[g], bounds[g + 1]
-        mx = tuple(max(s[d] for s in shapes[lo:hi]) for d in range(ndim))
-        x = torch.empty((hi - lo, ) + mx, dtype=torch.float32, device=dev)
-        m = torch.empty((hi - lo, ) + mx, dtype=torch.int32, device=dev)
-        vol = cum(mx) if ndim else 1
-        for i in range(lo, hi):
-            dst[i] = x.data_ptr() + 4 * vol * (i - lo)
-            msk[i] = m.data_ptr() + 4 * vol * (i - lo)
-            padded.append(mx)
+        mx = shp[lo:hi].max(axis=0)
+        full = (hi - lo, ) + tuple(int(v) for v in mx)
+        x = torch.empty(full, dtype=_F32, device=dev)
+        m = torch.empty(full, dtype=torch.int32, device=dev)
+        step = 4 * int(np.prod(mx))
+        idx = np.arange(hi - lo, dtype=np.uint64) * np.uint64(step)
+        dst[lo:hi] = np.uint64(x.data_ptr()) + idx
+        msk[lo:hi] = np.uint64(m.data_ptr()) + idx
+        padded[lo:hi] = mx
         new_x.append(x)
         masks.append(m)
-    sh, pd = _shape3(shapes), _shape3(padded)
+    src = _ptr_table([t.data_ptr() for t in inputs])
+    sh, pd = _right3(shp), _right3(padded)
     with _abi.on_device(dev):
         _abi.check(
-            _abi.lib().hpc_rll_pad_batch(_table([t.data_ptr() for t in inputs]), _table(dst), _table(msk),
-                                         sh.ctypes.data, pd.ctypes.data, n, int(value), _abi.stream_of(inputs[0])),
+            _abi.lib().hpc_rll_pad_batch(src.ctypes.data, dst.ctypes.data, msk.ctypes.data, sh.ctypes.data,
+                                         pd.ctypes.data, n, int(value), _abi.stream_of(inputs[0])),
             "hpc_rll_pad_batch")
     return new_x, masks
 
 
-def _split(inputs, ndim, group, group_mode):
-    shp = np.ascontiguousarray([list(t.shape) for t in inputs], dtype=np.int64)
-    n = len(inputs)
+def _split(shp, group, group_mode):
+    n, ndim = shp.shape
+    shp = np.ascontiguousarray(shp)
     L = _abi.lib()
     if group_mode == 'oracle':
         g = min(group, n)
         pos = np.zeros(g + 1, dtype=np.int64)
         _abi.check(L.hpc_rll_oracle_split_group(shp.ctypes.data, n, ndim, g, pos.ctypes.data), "oracle_split_group")
-        return [int(p) for p in pos]
+        return pos.tolist()
     starts = np.zeros(group + 2, dtype=np.int64)
     cnt = ctypes.c_int(0)
     _abi.check(
         L.hpc_rll_sample_split_group(shp.ctypes.data, n, ndim, group, next(_seed), starts.ctypes.data,
                                      ctypes.byref(cnt)), "sample_split_group")
-    return [int(p) for p in starts[:cnt.value + 1]]
-
-
-def _flat_shapes(inputs, lo, hi):
-    out = []
-    for t in inputs[lo:hi]:
-        out.extend(int(d) for d in t.shape)
-    return out
+    return starts[:cnt.value + 1].tolist()
 
 
 def _padding(inputs, ndim, mode, value, group, group_mode):
     assert mode in ['constant'], mode
     assert group_mode in ['sample', 'oracle'], group_mode
     assert group >= 1, group
-    inputs = _check_inputs(inputs, ndim)
+    if _ext is not None and len(inputs) > 0 and inputs[0].is_cuda:
+        try:
+            if group > 1:
+                return _ext.group_pad_nd(list(inputs), ndim, group, 1 if group_mode == 'oracle' else 0, int(value))
+            new_x, mask, shapes = _ext.pad_nd(list(inputs), ndim, int(value))
+            return new_x, mask, shapes
+        except RuntimeError as e:  # TORCH_CHECK failures: map to the exception types of the ctypes path
+            msg = str(e)
+            if "float32" in msg:
+                raise TypeError(msg) from None
+            if "-D tensors" in msg or "one CUDA device" in msg:
+                raise ValueError(msg) from None
+            raise
+    inputs, shp = _prepare(inputs, ndim)
     if group > 1:
-        inputs = sorted(inputs, key=lambda t: cum(t.shape))
-        bounds = _split(inputs, ndim, group, group_mode)
-        new_x, mask = _pad_groups(inputs, ndim, bounds, value)
-        shapes = [_flat_shapes(inputs, bounds[g], bounds[g + 1]) for g in range(len(bounds) - 1)]
+        order = np.argsort(shp.prod(axis=1), kind="stable")  # == sorted(key=numel), stable like Python's sort
+        inputs = [inputs[i] for i in order]
+        shp = shp[order]
+        bounds = _split(shp, group, group_mode)
+        new_x, mask = _pad_groups(inputs, shp, bounds, value)
+        shapes = [shp[bounds[g]:bounds[g + 1]].reshape(-1).tolist() for g in range(len(bounds) - 1)]
         return [tuple(new_x), tuple(mask), tuple(shapes)]
-    new_x, mask = _pad_groups(inputs, ndim, [0, len(inputs)], value)
-    return new_x[0], mask[0], _flat_shapes(inputs, 0, len(inputs))
+    new_x, mask = _pad_groups(inputs, shp, [0, len(inputs)], value)
+    return new_x[0], mask[0], shp.reshape(-1).tolist()
 
 
 def _unpad_one(x, shapes, ndim):
     assert x.is_cuda, "hpc version only supports cuda"
-    if x.dtype != torch.float32:
+    if _ext is not None:
+        return _ext.unpad_nd(x, [int(v) for v in shapes], ndim)
+    if x.dtype is not _F32:
         raise TypeError("padding supports float32 tensors")
-    x = x.contiguous()
+    if not x.is_contiguous():
+        x = x.contiguous()
     n = x.shape[0]
-    shp = [tuple(int(v) for v in shapes[i * ndim:(i + 1) * ndim]) for i in range(n)]
-    if len(shapes) != n * ndim:
+    shp = np.asarray(shapes, dtype=np.int64)
+    if shp.size != n * ndim:
         raise ValueError("shapes must hold %d ints per tensor" % ndim)
-    outs = [torch.empty(s, dtype=torch.float32, device=x.device) for s in shp]
-    vol = cum(x.shape[1:])
-    src = [x.data_ptr() + 4 * vol * i for i in range(n)]
-    sh, pd = _shape3(shp), _shape3([tuple(x.shape[1:])] * n)
+    shp = shp.reshape(n, ndim)
+    sizes = shp.prod(axis=1)
+    flat = torch.empty(int(sizes.sum()), dtype=_F32, device=x.device)  # one allocation, outputs are views
+    offs = np.zeros(n, dtype=np.uint64)
+    np.cumsum(sizes[:-1], out=offs[1:].view(np.int64)) if n > 1 else None
+    dst = np.uint64(flat.data_ptr()) + offs * np.uint64(4)
+    vol = 4 * cum(x.shape[1:])
+    src = np.uint64(x.data_ptr()) + np.arange(n, dtype=np.uint64) * np.uint64(vol)
+    pad3 = _right3(np.broadcast_to(np.array(x.shape[1:], dtype=np.int64), (n, ndim)))
+    sh3 = _right3(shp)
     with _abi.on_device(x.device):
         _abi.check(
-            _abi.lib().hpc_rll_unpad_batch(_table(src), _table([o.data_ptr() for o in outs]), sh.ctypes.data,
-                                           pd.ctypes.data, n, _abi.stream_of(x)), "hpc_rll_unpad_batch")
-    return outs
+            _abi.lib().hpc_rll_unpad_batch(src.ctypes.data, dst.ctypes.data, sh3.ctypes.data, pad3.ctypes.data, n,
+                                           _abi.stream_of(x)), "hpc_rll_unpad_batch")
+    pieces = flat.split(sizes.tolist())
+    if ndim == 1:
+        return list(pieces)
+    return [p.view(s) for p, s in zip(pieces, shp.tolist())]
 
 
 def _unpadding(x, shapes, ndim):
     if isinstance(x, torch.Tensor):
-        return _unpad_one(x, list(shapes), ndim)
+        return _unpad_one(x, shapes, ndim)
     ret = []
     for t, s in zip(x, shapes):
-        ret.append(_unpad_one(t, list(s), ndim))
-    return sum(ret, [])
+        ret.extend(_unpad_one(t, s, ndim))
+    return ret
 
 
 def Padding1D(inputs: List[torch.Tensor], mode='constant', value: int = 0, group: int = 1, group_mode='sample'):

@@ -202,7 +202,7 @@ int hpc_rll_iqn_nstep_td_backward(const float* grad_loss, const float* grad_buf,
  * replaces Pad{1,2,3}DForward / GroupPad{1,2,3}DForward / Unpad{1,2,3}DForward and the two group splitters
  * (/root/reference/src/rl_utils/padding.cu:8-589, kernels include/hpc/rll/cuda/rl_utils/padding_kernel.h:100-233);
  * semantics of hpc_rll/origin/padding.py.  Descriptor tables are HOST arrays of length n (device pointers
- * inside); shapes / padded are n x 3 int32 (trailing dims 1 for 1-D / 2-D).  No allocation, no copy: the
+ * inside); shapes / padded are n x 3 int32, right-aligned (leading dims 1 for 1-D / 2-D).  No allocation, no copy: the
  * tables ride in kernel parameter space.
  *   pad  : dst[k] (padded slot, prod(padded[k]) floats) = src[k] inside shapes[k], `value` elsewhere;
  *          mask[k] (int32) = 1 inside, `value` elsewhere

@@ -109,3 +109,40 @@ def test_padding_argument_errors():
         pad([torch.zeros(3, 3, dtype=torch.float64).cuda()])
     with pytest.raises(AssertionError):
         pad([torch.zeros(3, 3)])
+
+
+def test_reference_named_pybind_bindings():
+    """The thin torch/pybind layer exports the reference's 11 padding bindings (src/rl_utils/entry.cpp:9-20)
+    with the same call conventions as hpc_rll/rl_utils/padding.py uses them."""
+    need_cuda()
+    import di_hpc_b200.rl_utils.padding as P
+    E = P._ext
+    assert E is not None, "hpc_rl_utils_b200 extension missing (python -m di_hpc_b200.build_torch_ext)"
+    rng = np.random.default_rng(3)
+    shapes = [(int(rng.integers(3, 9)), int(rng.integers(2, 7))) for _ in range(20)]
+    data = [torch.randn(*s).cuda() for s in shapes]
+    x, m = E.Pad2DForward(data, 0)
+    ox, om, _ = po.pad([host(d) for d in data])
+    assert np.array_equal(host(x), ox) and np.array_equal(host(m), om)
+    flat = [int(v) for s in shapes for v in s]
+    for a, b in zip(E.Unpad2DForward(x, flat), data):
+        assert a.eq(b).all()
+    srt = sorted(data, key=lambda t: t.numel())
+    res = E.oracle_split_group(srt, 3)
+    group_shape, group_idx = res[:-1], res[-1]
+    assert len(group_idx) == len(group_shape) + 1 == 4 and group_idx[0] == 0 and group_idx[-1] == len(srt)
+    for g, shp in enumerate(group_shape):
+        grp = srt[group_idx[g]:group_idx[g + 1]]
+        assert list(shp) == [max(t.shape[0] for t in grp), max(t.shape[1] for t in grp)]
+    res_s = E.sample_split_group(srt, 4)
+    assert res_s[-1][0] == 0 and res_s[-1][-1] == len(srt) and len(res_s) - 1 <= 4
+    cnt = [group_idx[i + 1] - group_idx[i] for i in range(3)]
+    mx = [v for s in group_shape for v in s]
+    gid = [g for g in range(3) for _ in range(cnt[g])]
+    gx, gm = E.GroupPad2DForward(srt, cnt, mx, gid, group_idx, 0)
+    assert len(gx) == 3 and [t.shape[0] for t in gx] == cnt
+    k = 0
+    for g in range(3):
+        ogx, ogm, _ = po.pad([host(t) for t in srt[k:k + cnt[g]]])
+        assert np.array_equal(host(gx[g]), ogx) and np.array_equal(host(gm[g]), ogm)
+        k += cnt[g]
