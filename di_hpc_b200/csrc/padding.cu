@@ -36,28 +36,56 @@ struct PadBatch {
 // Shapes are right-aligned into 3 dims (1-D: (1,1,L); 2-D: (1,A,B)), so an item is a list of ROWS of
 // d2 contiguous elements.  One warp per row at a time, lanes along the row: no per-element division,
 // coalesced reads and writes; rows are spread over the 8 warps of a CTA and over gridDim.y CTAs.
-template <bool UNPAD>
+template <bool UNPAD, bool VEC>
 __global__ void __launch_bounds__(256) pad_kernel(const __grid_constant__ PadBatch batch, float value, int ivalue) {
     const PadItem& p = batch.it[blockIdx.x];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int s0 = p.s[0], s1 = p.s[1], s2 = p.s[2], m1 = p.m[1], m2 = p.m[2];
-    const int d0 = UNPAD ? s0 : p.m[0], d1 = UNPAD ? s1 : m1, d2 = UNPAD ? s2 : m2;
+    const int d0 = UNPAD ? s0 : p.m[0], d1 = UNPAD ? s1 : m1;
     const int64_t rows = static_cast<int64_t>(d0) * d1;
     for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + warp; r < rows; r += static_cast<int64_t>(gridDim.y) * 8) {
         const int a = static_cast<int>(r / d1), b = static_cast<int>(r - static_cast<int64_t>(a) * d1);
         if (UNPAD) {
             const float* __restrict__ src = p.src + (static_cast<int64_t>(a) * m1 + b) * m2;
             float* __restrict__ dst = p.dst + r * s2;
-            for (int c = lane; c < s2; c += 32) dst[c] = __ldg(src + c);
+            if (VEC) {  // padded rows are 16-byte aligned (m2 % 4 == 0): 128-bit loads, scalar stores
+                for (int c = lane * 4; c < s2; c += 128) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src + c));
+                    dst[c] = v.x;
+                    if (c + 1 < s2) dst[c + 1] = v.y;
+                    if (c + 2 < s2) dst[c + 2] = v.z;
+                    if (c + 3 < s2) dst[c + 3] = v.w;
+                }
+            } else {
+                for (int c = lane; c < s2; c += 32) dst[c] = __ldg(src + c);
+            }
         } else {
             const bool row_in = a < s0 && b < s1;
             const float* __restrict__ src = p.src + (static_cast<int64_t>(a) * s1 + b) * s2;
             float* __restrict__ dst = p.dst + r * m2;
             int32_t* __restrict__ msk = p.mask + r * m2;
-            for (int c = lane; c < m2; c += 32) {
-                const bool inside = row_in && c < s2;
-                dst[c] = inside ? __ldg(src + c) : value;
-                msk[c] = inside ? 1 : ivalue;
+            if (VEC) {  // scalar loads from the ragged source row, 128-bit stores of data and mask
+                const int lim = row_in ? s2 : 0;
+                for (int c = lane * 4; c < m2; c += 128) {
+                    float4 v;
+                    int4 k;
+                    v.x = c < lim ? __ldg(src + c) : value;
+                    v.y = c + 1 < lim ? __ldg(src + c + 1) : value;
+                    v.z = c + 2 < lim ? __ldg(src + c + 2) : value;
+                    v.w = c + 3 < lim ? __ldg(src + c + 3) : value;
+                    k.x = c < lim ? 1 : ivalue;
+                    k.y = c + 1 < lim ? 1 : ivalue;
+                    k.z = c + 2 < lim ? 1 : ivalue;
+                    k.w = c + 3 < lim ? 1 : ivalue;
+                    *reinterpret_cast<float4*>(dst + c) = v;
+                    *reinterpret_cast<int4*>(msk + c) = k;
+                }
+            } else {
+                for (int c = lane; c < m2; c += 32) {
+                    const bool inside = row_in && c < s2;
+                    dst[c] = inside ? __ldg(src + c) : value;
+                    msk[c] = inside ? 1 : ivalue;
+                }
             }
         }
     }
@@ -72,6 +100,7 @@ static int pad_batch(const float* const* src, float* const* dst, int32_t* const*
         const int cnt = static_cast<int>(std::min<int64_t>(kPadChunk, n - base));
         PadBatch batch;
         int64_t max_total = 1;
+        bool vec = true;  // every padded row 16-byte aligned?
         for (int i = 0; i < cnt; ++i) {
             PadItem& p = batch.it[i];
             const int64_t k = base + i;
@@ -91,15 +120,21 @@ static int pad_batch(const float* const* src, float* const* dst, int32_t* const*
             HPC_REQUIRE((own == 0 || p.src) && (tot == 0 || (p.dst && (unpad || p.mask))),
                         "pad: null tensor pointer at item %lld", (long long)k);
             max_total = std::max(max_total, tot);
+            const void* padded_base = unpad ? static_cast<const void*>(p.src) : static_cast<const void*>(p.dst);
+            vec = vec && (p.m[2] % 4 == 0) && aligned16(padded_base) && (unpad || aligned16(p.mask));
         }
         // ~2048 elements per CTA pass; enough CTAs per item to spread big tensors over the machine
         int64_t by = (max_total + 2047) / 2048;
         by = std::min<int64_t>(std::max<int64_t>(by, 1), 2048);
         const dim3 grid(static_cast<unsigned>(cnt), static_cast<unsigned>(by));
-        if (unpad)
-            pad_kernel<true><<<grid, 256, 0, stream>>>(batch, static_cast<float>(value), value);
-        else
-            pad_kernel<false><<<grid, 256, 0, stream>>>(batch, static_cast<float>(value), value);
+        const float fv = static_cast<float>(value);
+        if (unpad) {
+            if (vec) pad_kernel<true, true><<<grid, 256, 0, stream>>>(batch, fv, value);
+            else pad_kernel<true, false><<<grid, 256, 0, stream>>>(batch, fv, value);
+        } else {
+            if (vec) pad_kernel<false, true><<<grid, 256, 0, stream>>>(batch, fv, value);
+            else pad_kernel<false, false><<<grid, 256, 0, stream>>>(batch, fv, value);
+        }
         count_launch();
         HPC_LAUNCH_CHECK();
     }
