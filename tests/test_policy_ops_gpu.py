@@ -200,3 +200,28 @@ def test_ppo_dual_clip_must_exceed_one():
     with pytest.raises(AssertionError):
         PPO(8, 4)(*[dev(inp[k]) for k in ("logits_new", "logits_old", "action", "value_new", "value_old", "adv",
                                           "return_")], None, 0.2, True, 0.5)
+
+
+def test_masked_actions_with_minus_inf_logits():
+    """Illegal-action masking puts -inf into logits.  The row statistics must stay finite (the same guard
+    torch.distributions.Categorical applies, clamping to finfo.min) and equal the result of simply removing
+    the masked action: compare an N-action problem with one -inf column against the (N-1)-action oracle."""
+    need_cuda()
+    g = rng(77)
+    T, B, N = 6, 40, 9
+    inp = vtrace_inputs(g, T, B, N - 1, True)
+    coef = [1.0, 0.5, -0.25]
+    o = orc.vtrace(inp["target_output"], inp["behaviour_output"], inp["action"], inp["value"], inp["reward"],
+                   inp["weight"], coef=coef, **HP2)
+    k = 4  # masked column inserted at index k; actions >= k shift by one
+    big = dict(inp)
+    for name in ("target_output", "behaviour_output"):
+        big[name] = np.insert(inp[name], k, -np.inf, axis=2).astype(np.float32)
+    big["action"] = np.where(inp["action"] >= k, inp["action"] + 1, inp["action"]).astype(np.int64)
+    losses, gt, gv = run_vtrace(big, HP2, coef)
+    assert np.all(np.isfinite(losses)) and np.all(np.isfinite(gt)) and np.all(np.isfinite(gv))
+    for i, name in enumerate(("policy_loss", "value_loss", "entropy_loss")):
+        close(losses[i], o[name], name)
+    assert np.all(gt[:, :, k] == 0)
+    close(np.delete(gt, k, axis=2), o["grad_target_output"], "grad_target_output")
+    close(gv, o["grad_value"], "grad_value")

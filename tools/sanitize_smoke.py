@@ -1,0 +1,81 @@
+"""One small forward+backward of every op (and the padding path) -- the workload for
+`compute-sanitizer --tool memcheck|racecheck|synccheck python tools/sanitize_smoke.py`."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hpc_rll.rl_utils.gae import GAE  # noqa: E402
+from hpc_rll.rl_utils.padding import Padding2D, UnPadding2D  # noqa: E402
+from hpc_rll.rl_utils.ppo import PPO  # noqa: E402
+from hpc_rll.rl_utils.td import (DistNStepTD, IQNNStepTDError, QNStepTD, QNStepTDRescale, QRDQNNStepTDError,  # noqa: E402
+                                 TDLambda)
+from hpc_rll.rl_utils.upgo import UPGO  # noqa: E402
+from hpc_rll.rl_utils.vtrace import VTrace  # noqa: E402
+from di_hpc_b200 import _abi  # noqa: E402
+
+D = "cuda"
+ONE = torch.ones(1, device=D)
+
+
+def r(*s):
+    return torch.randn(*s, device=D)
+
+
+def main():
+    for T, B, N in ((37, 132, 6), (16, 260, 16), (9, 64, 40)):
+        v, rew = r(T + 1, B).requires_grad_(True), r(T, B).requires_grad_(True)
+        for cfg in (-1, 0, 2, 13, 20, 99):
+            _abi.set_config(0, cfg)
+            torch.autograd.grad(GAE(T, B)(v, rew), [v, rew], grad_outputs=r(T, B))
+        _abi.set_config(0, -1)
+        w = torch.rand(T, B, device=D)
+        for cfg in (-1, 99):
+            _abi.set_config(1, cfg)
+            torch.autograd.grad(TDLambda(T, B)(v, rew.detach(), w), [v], grad_outputs=ONE)
+        _abi.set_config(1, -1)
+        t = r(T, B, N).requires_grad_(True)
+        a = torch.randint(0, N, (T, B), device=D)
+        for cfg in (-1, 99):
+            _abi.set_config(2, cfg)
+            _abi.set_config(3, cfg)
+            l = VTrace(T, B, N)(t, r(T, B, N), a, v, rew.detach(), w)
+            torch.autograd.grad(l.policy_loss + l.value_loss + l.entropy_loss, [t, v], grad_outputs=ONE)
+            torch.autograd.grad(UPGO(T, B, N)(t, torch.rand(T, B, device=D), a, rew.detach(), v.detach()), [t],
+                                grad_outputs=ONE)
+        _abi.set_config(2, -1)
+        _abi.set_config(3, -1)
+        ln = r(B, N).requires_grad_(True)
+        vn = r(B).requires_grad_(True)
+        l, _ = PPO(B, N)(ln, r(B, N), a[0], vn, r(B), r(B), r(B), torch.rand(B, device=D), 0.2, True, 3.0)
+        torch.autograd.grad(l.policy_loss + l.value_loss + l.entropy_loss, [ln, vn], grad_outputs=ONE)
+        q = r(B, N).requires_grad_(True)
+        act, nact = a[0], torch.randint(0, N, (B, ), device=D)
+        done = (torch.rand(B, device=D) < 0.3).float()
+        for cls in (QNStepTD, QNStepTDRescale):
+            torch.autograd.grad(cls(T, B, N)(q, r(B, N), act, nact, rew.detach(), done, None, 0.95)[0], [q],
+                                grad_outputs=ONE)
+        d0 = torch.softmax(r(B, N, 51), -1).requires_grad_(True)
+        torch.autograd.grad(
+            DistNStepTD(T, B, N, 51)(d0, torch.softmax(r(B, N, 51), -1), act, nact, rew.detach(), done, None, 0.95, -10.,
+                                     10.)[0], [d0], grad_outputs=ONE)
+        for tau in (8, 39, 64):
+            qq = r(B, N, tau).requires_grad_(True)
+            torch.autograd.grad(QRDQNNStepTDError(tau, T, B, N)(qq, r(B, N, tau), act, nact, rew.detach(), done, 0.95)[0],
+                                [qq], grad_outputs=ONE)
+            qi = r(tau, B, N).requires_grad_(True)
+            torch.autograd.grad(
+                IQNNStepTDError(tau, tau + 1, T, B, N)(qi, r(tau + 1, B, N), act, nact, rew.detach(), done,
+                                                       torch.rand(tau, B, device=D), 0.95, 0.9)[0], [qi], grad_outputs=ONE)
+    data = [r(int(torch.randint(3, 20, (1, ))), int(torch.randint(2, 17, (1, )))) for _ in range(40)]
+    x, m, s = Padding2D(data)
+    UnPadding2D(x, s)
+    gx, gm, gs = Padding2D(data, group=4, group_mode='oracle')
+    UnPadding2D(gx, gs)
+    torch.cuda.synchronize()
+    print("sanitize_smoke done, kernel launches:", _abi.launch_count())
+
+
+if __name__ == "__main__":
+    main()
