@@ -233,3 +233,29 @@ def test_iqn_vs_golden(name):
         close(loss, c.out("loss", prec), "loss")
         close(td, c.out("td_error_per_sample", prec), "td")
         close(gq, c.grad("q", prec), "grad_q")
+
+
+@pytest.mark.parametrize("cfg", [0, 1])
+def test_dist_kernel_variants(cfg):
+    """warp-per-sample (0) and lane-per-sample (1) C51 kernels against the oracle, incl. done=1 rows whose whole
+    mass lands on one atom and a batch that is not a multiple of the 128-sample tile."""
+    need_cuda()
+    from di_hpc_b200 import _abi
+    g = rng(cfg + 900)
+    T, B, N, n_atom = 3, 300, 5, 51
+    inp = base_inputs(g, T, B, N, True)
+    inp["reward"] = (inp["reward"] * 4).astype(np.float32)
+    inp["dist"] = softmax(g.standard_normal((B, N, n_atom)))
+    inp["next_n_dist"] = softmax(g.standard_normal((B, N, n_atom)))
+    try:
+        _abi.set_config(_abi.OP_DIST_NSTEP_TD, cfg)
+        loss, td, gd = run_dist(inp, 0.99, -10.0, 10.0, 1.0)
+        loss_b, td_b, gd_b = run_dist(inp, 0.99, -10.0, 10.0, 1.0)
+    finally:
+        _abi.set_config(_abi.OP_DIST_NSTEP_TD, -1)
+    o = orc.dist_nstep_td(inp["dist"], inp["next_n_dist"], inp["action"], inp["next_n_action"], inp["reward"],
+                          inp["done"], inp["weight"], 0.99, -10.0, 10.0, 1.0)
+    close(loss, o["loss"], "loss")
+    close(td, o["td_error_per_sample"], "td")
+    close(gd, o["grad_dist"], "grad_dist")
+    assert loss == loss_b and np.array_equal(td, td_b) and np.array_equal(gd, gd_b)  # run-to-run reproducible

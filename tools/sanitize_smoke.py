@@ -53,6 +53,11 @@ def main():
         q = r(B, N).requires_grad_(True)
         act, nact = a[0], torch.randint(0, N, (B, ), device=D)
         done = (torch.rand(B, device=D) < 0.3).float()
+        for dcfg in (0, 1):
+            _abi.set_config(6, dcfg)
+            dd = torch.softmax(r(B, N, 21), -1).requires_grad_(True)
+            torch.autograd.grad(DistNStepTD(T, B, N, 21)(dd, torch.softmax(r(B, N, 21), -1), act, nact, rew.detach(), done, None, 0.9, -3., 3.)[0], [dd], grad_outputs=ONE)
+        _abi.set_config(6, -1)
         for cls in (QNStepTD, QNStepTDRescale):
             torch.autograd.grad(cls(T, B, N)(q, r(B, N), act, nact, rew.detach(), done, None, 0.95)[0], [q],
                                 grad_outputs=ONE)
