@@ -52,7 +52,7 @@ def main():
     adv_f = GAE(T, B)(val, rew)
 
     def rel(a, b):
-        return float((a.double() - b.double()).abs().max() / max(1.0, float(b.double().abs().max())))
+        return float((a.detach().double() - b.detach().double()).abs().max() / max(1.0, float(b.detach().double().abs().max())))
 
     out["vtrace_losses"] = max(rel(pg, lf.policy_loss), rel(vl, lf.value_loss), rel(ent, lf.entropy_loss))
     out["vtrace_grad_target"] = rel(gt_l, gt_f[:, b0:b1])
