@@ -133,6 +133,48 @@ __global__ void __launch_bounds__(256, KMAX >= 8 ? 1 : 3) ppo_rows_fwd(const flo
     }
 }
 
+// staged variant (N <= 32, not 128-bit eligible): see softmax_rows.cuh "Staged rows"
+__global__ void __launch_bounds__(kStageRows) ppo_rows_fwd_staged(
+    const float* __restrict__ logits_new, const float* __restrict__ logits_old, const int64_t* __restrict__ action,
+    const float* __restrict__ value_new, const float* __restrict__ value_old, const float* __restrict__ adv,
+    const float* __restrict__ ret, const float* __restrict__ weight, float* __restrict__ pol_coef,
+    float* __restrict__ val_coef, double* __restrict__ partials, const PpoParams P, int64_t R, int N, int pitch,
+    int aligned) {
+    extern __shared__ float tiles[];
+    __shared__ double red[5 * 32];
+    float* tn = tiles;
+    float* to = tiles + kStageRows * pitch;
+    double acc[5] = {0, 0, 0, 0, 0};
+    const int64_t ntiles = (R + kStageRows - 1) / kStageRows;
+    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const int64_t row0 = tix * kStageRows, row = row0 + threadIdx.x;
+        __syncthreads();
+        stage_rows(logits_new, R, N, pitch, row0, tn, aligned != 0);
+        stage_rows(logits_old, R, N, pitch, row0, to, aligned != 0);
+        __syncthreads();
+        if (row < R) {
+            const float* xn = tn + threadIdx.x * pitch;
+            const float* xo = to + threadIdx.x * pitch;
+            float mn, sn, t1, mo, so, t2;
+            staged_stats<true>(xn, N, mn, sn, t1);
+            staged_stats<false>(xo, N, mo, so, t2);
+            const float lsn = logf(sn), lso = logf(so);
+            const float H = lsn - t1 / sn;
+            const int a = static_cast<int>(action[row]);
+            float pc, vc;
+            ppo_sample(P, row_logp<true>(xn[a], mn, lsn), row_logp<true>(xo[a], mo, lso), H, adv[row], value_new[row],
+                       value_old[row], ret[row], weight ? weight[row] : 1.f, acc, pc, vc);
+            pol_coef[row] = pc;
+            val_coef[row] = vc;
+        }
+    }
+    block_sum<5>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) partials[static_cast<size_t>(k) * gridDim.x + blockIdx.x] = acc[k];
+    }
+}
+
 __global__ void __launch_bounds__(256) ppo_rows_fwd_loop(const float* __restrict__ logits_new,
                                                           const float* __restrict__ logits_old,
                                                           const int64_t* __restrict__ action,
@@ -219,12 +261,19 @@ int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const 
     const RowGeom ge = row_geom(N, aligned16(logits_new) && aligned16(logits_old));
     int log2G = 0;
     while ((1 << log2G) < ge.G) ++log2G;
-    const unsigned grid = rows_grid(B, ge.kmax == 0 ? 8 : (32 / ge.G) * 8);
+    const bool staged = use_staged_rows(N, ge.vec != 0);
+    const unsigned grid = rows_grid(B, staged ? kStageRows : (ge.kmax == 0 ? 8 : (32 / ge.G) * 8));
     const int n = static_cast<int>(N);
 #define HPC_PPO_ROWS(K, V)                                                                                       \
     ppo_rows_fwd<K, V><<<grid, 256, 0, stream>>>(logits_new, logits_old, action, value_new, value_old, adv, return_, \
                                                  weight, pol_coef, val_coef, partials, P, B, n, ge.G, log2G)
-    if (ge.kmax == 0)
+    if (staged) {
+        static SmemOptIn opt;
+        if (int rc0 = opt.ensure(ppo_rows_fwd_staged, static_cast<int>(stage_bytes(31, 2)))) return rc0;  // largest pitch
+        ppo_rows_fwd_staged<<<grid, kStageRows, stage_bytes(n, 2), stream>>>(
+            logits_new, logits_old, action, value_new, value_old, adv, return_, weight, pol_coef, val_coef, partials, P, B,
+            n, stage_pitch(n), aligned16(logits_new) && aligned16(logits_old) ? 1 : 0);
+    } else if (ge.kmax == 0)
         ppo_rows_fwd_loop<<<grid, 256, 0, stream>>>(logits_new, logits_old, action, value_new, value_old, adv, return_,
                                                     weight, pol_coef, val_coef, partials, P, B, n);
     else

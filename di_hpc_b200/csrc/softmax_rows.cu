@@ -71,6 +71,43 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
     }
 }
 
+// Staged variant (N <= 32, not 128-bit eligible): see softmax_rows.cuh "Staged rows".
+template <bool ENT, bool CAT>
+__global__ void __launch_bounds__(kStageRows) softmax_grad_rows_staged_kernel(
+    const float* __restrict__ logits, const int64_t* __restrict__ action, const float* __restrict__ c1,
+    const float* __restrict__ w, const float* __restrict__ g1, const float* __restrict__ g2, float inv_n,
+    float* __restrict__ grad, int64_t R, int N, int P, int aligned) {
+    extern __shared__ float tile[];
+    const float s1 = __ldg(g1);
+    const float s2 = ENT ? __ldg(g2) * inv_n : 0.f;
+    const int64_t ntiles = (R + kStageRows - 1) / kStageRows;
+    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const int64_t row0 = tix * kStageRows, row = row0 + threadIdx.x;
+        __syncthreads();  // the previous tile has been written back
+        stage_rows(logits, R, N, P, row0, tile, aligned != 0);
+        __syncthreads();
+        if (row < R) {
+            float* x = tile + threadIdx.x * P;
+            float m, s, t;
+            staged_stats<ENT>(x, N, m, s, t);
+            const float logs = logf(s), inv_s = 1.f / s;
+            const float H = logs - t * inv_s;
+            const int a = static_cast<int>(action[row]);
+            const float c = s1 * c1[row];
+            const float e2 = ENT ? s2 * (w ? w[row] : 1.f) : 0.f;
+            for (int k = 0; k < N; ++k) {
+                const float xv = x[k];
+                const float p = expf(fmaxf(xv - m, kNegBig)) * inv_s;
+                float gq = c * ((k == a ? 1.f : 0.f) - p);
+                if (ENT) gq += e2 * (-p * (fmaxf(row_logp<CAT>(xv, m, logs), kNegBig) + H));
+                x[k] = gq;
+            }
+        }
+        __syncthreads();
+        unstage_rows(grad, R, N, P, row0, tile, aligned != 0);
+    }
+}
+
 // N too large for the register-resident path: one warp per row, strided passes over the row.
 template <bool ENT, bool CAT>
 __global__ void __launch_bounds__(256) softmax_grad_rows_loop_kernel(const float* __restrict__ logits,
@@ -119,6 +156,16 @@ static int launch_grad_t(const float* logits, const int64_t* action, const float
                          const float* g1, const float* g2, float inv_n, float* grad, int64_t R, int N,
                          cudaStream_t stream) {
     const RowGeom ge = row_geom(N, aligned16(logits) && aligned16(grad));
+    if (use_staged_rows(N, ge.vec != 0)) {
+        const int P = stage_pitch(N);
+        const unsigned sgrid = rows_grid(R, kStageRows);
+        const int al = aligned16(logits) && aligned16(grad) ? 1 : 0;
+        softmax_grad_rows_staged_kernel<ENT, CAT><<<sgrid, kStageRows, stage_bytes(N, 1), stream>>>(
+            logits, action, c1, w, g1, g2, inv_n, grad, R, N, P, al);
+        count_launch();
+        HPC_LAUNCH_CHECK();
+        return HPC_RLL_OK;
+    }
     int log2G = 0;
     while ((1 << log2G) < ge.G) ++log2G;
     const int rows_per_block = (32 / ge.G) * 8;

@@ -124,6 +124,100 @@ __device__ __forceinline__ float row_logp(float x, float m, float logs) {
     return CATEGORICAL ? x - (m + logs) : (x - m) - logs;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Staged rows: action counts that are not a multiple of 4 (Atari's 6 / 9 / 18 ...) cannot use 128-bit
+// row chunks, and scalar per-lane chunks waste lanes and shuffles.  For N <= 32 such tensors are instead
+// read as a FLAT contiguous stream: a CTA copies kStageRows consecutive rows (kStageRows*N floats, 128-bit
+// coalesced, row boundaries ignored) into shared memory with an odd pitch, then every thread owns ONE row
+// (bank-conflict-free column walk, no shuffles, all lanes busy).  Gradients go back the same way.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kStageRows = 256;
+inline int stage_pitch(int N) { return N | 1; }
+inline bool use_staged_rows(int64_t N, bool vec_eligible) { return N <= 32 && !vec_eligible; }
+inline size_t stage_bytes(int N, int tiles) { return static_cast<size_t>(tiles) * kStageRows * stage_pitch(N) * sizeof(float); }
+
+// copy rows [row0, row0 + kStageRows) of a contiguous (R, N) tensor into tile[r * P + c]
+__device__ __forceinline__ void stage_rows(const float* __restrict__ g, int64_t R, int N, int P, int64_t row0,
+                                           float* __restrict__ tile, bool aligned) {
+    const int64_t rows = min(static_cast<int64_t>(kStageRows), R - row0);
+    const int cnt = static_cast<int>(rows) * N;  // <= 256 * 32
+    const float* __restrict__ src = g + row0 * N;
+    const float invN = 1.f / static_cast<float>(N);
+    if (aligned) {  // (row0 * N) % 4 == 0 because row0 is a multiple of kStageRows
+        for (int i = threadIdx.x * 4; i < cnt; i += kStageRows * 4) {
+            int r = __float2int_rd((static_cast<float>(i) + 0.5f) * invN);  // exact for i < 2^13, N <= 32
+            int c = i - r * N;
+            if (i + 3 < cnt) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+                const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    tile[r * P + c] = e[q];
+                    if (++c == N) c = 0, ++r;
+                }
+            } else {
+                for (int q = 0; i + q < cnt; ++q) {
+                    tile[r * P + c] = __ldg(src + i + q);
+                    if (++c == N) c = 0, ++r;
+                }
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += kStageRows) {
+            const int r = __float2int_rd((static_cast<float>(i) + 0.5f) * invN);
+            tile[r * P + (i - r * N)] = __ldg(src + i);
+        }
+    }
+}
+
+// inverse: write tile rows back to a contiguous (R, N) tensor
+__device__ __forceinline__ void unstage_rows(float* __restrict__ g, int64_t R, int N, int P, int64_t row0,
+                                             const float* __restrict__ tile, bool aligned) {
+    const int64_t rows = min(static_cast<int64_t>(kStageRows), R - row0);
+    const int cnt = static_cast<int>(rows) * N;
+    float* __restrict__ dst = g + row0 * N;
+    const float invN = 1.f / static_cast<float>(N);
+    if (aligned) {
+        for (int i = threadIdx.x * 4; i < cnt; i += kStageRows * 4) {
+            int r = __float2int_rd((static_cast<float>(i) + 0.5f) * invN);
+            int c = i - r * N;
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (i + q < cnt) e[q] = tile[r * P + c];
+                if (++c == N) c = 0, ++r;
+            }
+            if (i + 3 < cnt) {
+                st_stream4(reinterpret_cast<float4*>(dst + i), make_float4(e[0], e[1], e[2], e[3]));
+            } else {
+                for (int q = 0; i + q < cnt; ++q) dst[i + q] = e[q];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += kStageRows) {
+            const int r = __float2int_rd((static_cast<float>(i) + 0.5f) * invN);
+            dst[i] = tile[r * P + (i - r * N)];
+        }
+    }
+}
+
+// statistics of one row sitting in shared memory (one thread per row)
+template <bool WANT_T>
+__device__ __forceinline__ void staged_stats(const float* __restrict__ x, int N, float& m, float& s, float& t) {
+    float mm = x[0];
+    for (int k = 1; k < N; ++k) mm = fmaxf(mm, x[k]);
+    float ss = 0.f, tt = 0.f;
+    for (int k = 0; k < N; ++k) {
+        const float d = fmaxf(x[k] - mm, kNegBig);
+        const float e = expf(d);
+        ss += e;
+        if (WANT_T) tt = fmaf(e, d, tt);
+    }
+    m = mm;
+    s = ss;
+    t = tt;
+}
+
 #endif  // __CUDACC__
 
 // ---- shared backward: grad[r,k] = (g1*c1[r])*(1[k=a_r]-p_k) + (g2*w_r*inv_n)*(-p_k(logp_k+H)) ----------

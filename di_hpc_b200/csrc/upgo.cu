@@ -58,6 +58,27 @@ __global__ void __launch_bounds__(256) upgo_rows_fwd(const float* __restrict__ l
     }
 }
 
+// staged variant (N <= 32, not 128-bit eligible): see softmax_rows.cuh "Staged rows"
+__global__ void __launch_bounds__(kStageRows) upgo_rows_fwd_staged(const float* __restrict__ logits,
+                                                                    const int64_t* __restrict__ action,
+                                                                    float* __restrict__ metric, int64_t R, int N, int P,
+                                                                    int aligned) {
+    extern __shared__ float tile[];
+    const int64_t ntiles = (R + kStageRows - 1) / kStageRows;
+    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const int64_t row0 = tix * kStageRows, row = row0 + threadIdx.x;
+        __syncthreads();
+        stage_rows(logits, R, N, P, row0, tile, aligned != 0);
+        __syncthreads();
+        if (row < R) {
+            const float* x = tile + threadIdx.x * P;
+            float m, s, t;
+            staged_stats<false>(x, N, m, s, t);
+            metric[row] = row_logp<false>(x[action[row]], m, logf(s));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) upgo_rows_fwd_loop(const float* __restrict__ logits,
                                                            const int64_t* __restrict__ action,
                                                            float* __restrict__ metric, int64_t R, int N) {
@@ -210,10 +231,15 @@ int hpc_rll_upgo_forward(const float* target_output, const float* rhos, const in
     const RowGeom ge = row_geom(N, aligned16(target_output));
     int log2G = 0;
     while ((1 << log2G) < ge.G) ++log2G;
-    const unsigned grid1 = rows_grid(R, ge.kmax == 0 ? 8 : (32 / ge.G) * 8);
+    const bool staged = use_staged_rows(N, ge.vec != 0);
+    const unsigned grid1 = rows_grid(R, staged ? kStageRows : (ge.kmax == 0 ? 8 : (32 / ge.G) * 8));
     const int n = static_cast<int>(N);
 #define HPC_UP_ROWS(K, V) upgo_rows_fwd<K, V><<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n, ge.G, log2G)
-    if (ge.kmax == 0) upgo_rows_fwd_loop<<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n);
+    if (staged)
+        upgo_rows_fwd_staged<<<grid1, kStageRows, stage_bytes(n, 1), stream>>>(target_output, action, metric, R, n,
+                                                                               stage_pitch(n),
+                                                                               aligned16(target_output) ? 1 : 0);
+    else if (ge.kmax == 0) upgo_rows_fwd_loop<<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n);
     else HPC_ROW_DISPATCH(ge, HPC_UP_ROWS);
 #undef HPC_UP_ROWS
     count_launch();

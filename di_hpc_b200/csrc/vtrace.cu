@@ -87,6 +87,47 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__
     if (threadIdx.x == 0) partials[blockIdx.x] = v[0];
 }
 
+// staged variant (N <= 32, not 128-bit eligible): see softmax_rows.cuh "Staged rows"
+__global__ void __launch_bounds__(kStageRows) vtrace_rows_fwd_staged(const float* __restrict__ target,
+                                                                      const float* __restrict__ behaviour,
+                                                                      const int64_t* __restrict__ action,
+                                                                      const float* __restrict__ weight,
+                                                                      float* __restrict__ is_out,
+                                                                      float* __restrict__ logp_out,
+                                                                      double* __restrict__ partials, int64_t R, int N,
+                                                                      int P, int aligned) {
+    extern __shared__ float tiles[];
+    __shared__ double red[32];
+    float* tt = tiles;
+    float* tb = tiles + kStageRows * P;
+    double ent_acc = 0.0;
+    const int64_t ntiles = (R + kStageRows - 1) / kStageRows;
+    for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
+        const int64_t row0 = tix * kStageRows, row = row0 + threadIdx.x;
+        __syncthreads();
+        stage_rows(target, R, N, P, row0, tt, aligned != 0);
+        stage_rows(behaviour, R, N, P, row0, tb, aligned != 0);
+        __syncthreads();
+        if (row < R) {
+            const float* xt = tt + threadIdx.x * P;
+            const float* xb = tb + threadIdx.x * P;
+            float mt, st, t1, mb, sb, t2;
+            staged_stats<true>(xt, N, mt, st, t1);
+            staged_stats<false>(xb, N, mb, sb, t2);
+            const float lst = logf(st), lsb = logf(sb);
+            const float H = lst - t1 / st;
+            const int a = static_cast<int>(action[row]);
+            const float selt = row_logp<true>(xt[a], mt, lst), selb = row_logp<true>(xb[a], mb, lsb);
+            is_out[row] = expf(selt - selb);
+            logp_out[row] = selt;
+            ent_acc += static_cast<double>(H * (weight ? weight[row] : 1.f));
+        }
+    }
+    double v[1] = {ent_acc};
+    block_sum<1>(v, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = v[0];
+}
+
 // N too large for registers: one warp per row, strided passes
 __global__ void __launch_bounds__(256) vtrace_rows_fwd_loop(const float* __restrict__ target,
                                                              const float* __restrict__ behaviour,
@@ -315,12 +356,19 @@ int hpc_rll_vtrace_forward(const float* target_output, const float* behaviour_ou
     int log2G = 0;
     while ((1 << log2G) < ge.G) ++log2G;
     const int rows_per_block = (32 / ge.G) * 8;
-    const unsigned grid1 = rows_grid(R, ge.kmax == 0 ? 8 : rows_per_block);
+    const bool staged = use_staged_rows(N, ge.vec != 0);
+    const unsigned grid1 = rows_grid(R, staged ? kStageRows : (ge.kmax == 0 ? 8 : rows_per_block));
     const int n = static_cast<int>(N);
 #define HPC_VT_ROWS(K, V)                                                                                       \
     vtrace_rows_fwd<K, V><<<grid1, 256, 0, stream>>>(target_output, behaviour_output, action, weight, is_buf,   \
                                                      logp_buf, partials, R, n, ge.G, log2G)
-    if (ge.kmax == 0)
+    if (staged) {
+        static SmemOptIn opt;
+        if (int rc0 = opt.ensure(vtrace_rows_fwd_staged, static_cast<int>(stage_bytes(31, 2)))) return rc0;  // largest pitch
+        vtrace_rows_fwd_staged<<<grid1, kStageRows, stage_bytes(n, 2), stream>>>(
+            target_output, behaviour_output, action, weight, is_buf, logp_buf, partials, R, n, stage_pitch(n),
+            aligned16(target_output) && aligned16(behaviour_output) ? 1 : 0);
+    } else if (ge.kmax == 0)
         vtrace_rows_fwd_loop<<<grid1, 256, 0, stream>>>(target_output, behaviour_output, action, weight, is_buf,
                                                         logp_buf, partials, R, n);
     else

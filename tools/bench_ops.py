@@ -191,6 +191,10 @@ def main():
         ("td_lambda_now", lambda: bench_td_lambda(1024, 65536, it, use_w=False)),
         ("vtrace", lambda: bench_vtrace(512, 32768, 16, it)),
         ("vtrace128", lambda: bench_vtrace(512, 4096, 128, it)),
+        ("vtrace6", lambda: bench_vtrace(512, 32768, 6, it)),
+        ("vtrace18", lambda: bench_vtrace(512, 32768, 18, it)),
+        ("upgo6", lambda: bench_upgo(512, 32768, 6, it)),
+        ("ppo6", lambda: bench_ppo(1 << 22, 6, it)),
         ("upgo", lambda: bench_upgo(512, 32768, 16, it)),
         ("upgo128", lambda: bench_upgo(512, 4096, 128, it)),
         ("ppo", lambda: bench_ppo(1 << 22, 16, it)),
