@@ -133,7 +133,9 @@ __device__ __forceinline__ float row_logp(float x, float m, float logs) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int kStageRows = 256;
 inline int stage_pitch(int N) { return N | 1; }
-inline bool use_staged_rows(int64_t N, bool vec_eligible) { return N <= 32 && !vec_eligible; }
+// measured (profiles/r01_ops.md): for N <= 8 the per-lane scalar chunks are as fast or faster; from N = 9 the
+// staged path wins (N=18: 3.3 -> 2.0 ms for V-trace at T=512, B=32768)
+inline bool use_staged_rows(int64_t N, bool vec_eligible) { return N > 8 && N <= 32 && !vec_eligible; }
 inline size_t stage_bytes(int N, int tiles) { return static_cast<size_t>(tiles) * kStageRows * stage_pitch(N) * sizeof(float); }
 
 // copy rows [row0, row0 + kStageRows) of a contiguous (R, N) tensor into tile[r * P + c]
@@ -145,20 +147,21 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ g, int64_t 
     const float invN = 1.f / static_cast<float>(N);
     if (aligned) {  // (row0 * N) % 4 == 0 because row0 is a multiple of kStageRows
         for (int i = threadIdx.x * 4; i < cnt; i += kStageRows * 4) {
-            int r = __float2int_rd((static_cast<float>(i) + 0.5f) * invN);  // exact for i < 2^13, N <= 32
+            const int r = __float2int_rd((static_cast<float>(i) + 0.5f) * invN);  // exact for i < 2^13, N <= 32
             int c = i - r * N;
+            int idx = r * P + c;  // running shared-memory index: +1 per element, +(P-N) more at a row end
             if (i + 3 < cnt) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
                 const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    tile[r * P + c] = e[q];
-                    if (++c == N) c = 0, ++r;
+                    tile[idx++] = e[q];
+                    if (++c == N) c = 0, idx += P - N;
                 }
             } else {
                 for (int q = 0; i + q < cnt; ++q) {
-                    tile[r * P + c] = __ldg(src + i + q);
-                    if (++c == N) c = 0, ++r;
+                    tile[idx++] = __ldg(src + i + q);
+                    if (++c == N) c = 0, idx += P - N;
                 }
             }
         }
@@ -179,13 +182,15 @@ __device__ __forceinline__ void unstage_rows(float* __restrict__ g, int64_t R, i
     const float invN = 1.f / static_cast<float>(N);
     if (aligned) {
         for (int i = threadIdx.x * 4; i < cnt; i += kStageRows * 4) {
-            int r = __float2int_rd((static_cast<float>(i) + 0.5f) * invN);
+            const int r = __float2int_rd((static_cast<float>(i) + 0.5f) * invN);
             int c = i - r * N;
+            int idx = r * P + c;
             float e[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                if (i + q < cnt) e[q] = tile[r * P + c];
-                if (++c == N) c = 0, ++r;
+                if (i + q < cnt) e[q] = tile[idx];
+                ++idx;
+                if (++c == N) c = 0, idx += P - N;
             }
             if (i + 3 < cnt) {
                 st_stream4(reinterpret_cast<float4*>(dst + i), make_float4(e[0], e[1], e[2], e[3]));
