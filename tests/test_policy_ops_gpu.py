@@ -48,7 +48,10 @@ HP2 = dict(gamma=0.9, lambda_=0.8, rho_clip_ratio=1.5, c_clip_ratio=0.9, rho_pg_
 @pytest.mark.parametrize("T,B,N,use_w,hp", [(128, 128, 128, False, HP1), (16, 256, 16, True, HP2), (5, 7, 3, True, HP1),
                                              (1, 2, 1, False, HP1), (33, 132, 6, True, HP2), (9, 260, 40, False, HP1),
                                              (4, 64, 300, True, HP1), (12, 1024, 8, True, HP2), (6, 36, 1100, False, HP2),
-                                             (50, 4100, 4, False, HP1)])
+                                             (50, 4100, 4, False, HP1),
+                                             # staged-rows path (9 <= N <= 32, N % 4 != 0), partial last tile
+                                             (7, 300, 18, True, HP2), (3, 1000, 9, False, HP1), (2, 129, 31, True, HP1),
+                                             (11, 77, 13, False, HP2)])
 def test_vtrace_vs_oracle(T, B, N, use_w, hp):
     need_cuda()
     inp = vtrace_inputs(rng(T * 131 + B * 7 + N), T, B, N, use_w)
@@ -110,7 +113,8 @@ def run_upgo(inp, coef):
 
 
 @pytest.mark.parametrize("T,B,N", [(256, 256, 256), (16, 256, 16), (5, 7, 3), (1, 4, 3), (2, 4, 16), (33, 132, 6),
-                                   (20, 3, 33), (8, 1024, 8), (3, 40, 1100), (40, 4100, 4)])
+                                   (20, 3, 33), (8, 1024, 8), (3, 40, 1100), (40, 4100, 4), (7, 300, 18), (3, 1000, 9),
+                                   (2, 129, 31), (11, 77, 13)])
 def test_upgo_vs_oracle(T, B, N):
     need_cuda()
     g = rng(T * 17 + B * 3 + N)
@@ -162,7 +166,9 @@ def ppo_inputs(g, B, N, use_w):
 @pytest.mark.parametrize("B,N,use_w,clip,vclip,dual", [(128, 128, False, 0.2, True, None), (4096, 6, True, 0.2, True, 3.0),
                                                          (17, 16, True, 0.1, False, None), (5, 1, False, 0.2, True, 2.0),
                                                          (1000, 37, False, 0.3, False, 1.5), (300, 260, True, 0.2, True, None),
-                                                         (64, 1100, True, 0.2, True, 5.0), (70000, 8, True, 0.2, True, None)])
+                                                         (64, 1100, True, 0.2, True, 5.0), (70000, 8, True, 0.2, True, None),
+                                                         (3000, 18, True, 0.2, True, None), (257, 9, False, 0.2, False, 2.0),
+                                                         (1000, 31, True, 0.1, True, None)])
 def test_ppo_vs_oracle(B, N, use_w, clip, vclip, dual):
     need_cuda()
     inp = ppo_inputs(rng(B * 13 + N), B, N, use_w)
