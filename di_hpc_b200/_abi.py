@@ -27,6 +27,8 @@ SIGNATURES = {
     "hpc_rll_debug_set_config": (c_int, [c_int, c_int]),
     "hpc_rll_gae_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
     "hpc_rll_gae_backward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
+    "hpc_rll_gae_forward_moments": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_sz, c_vp]),
+    "hpc_rll_adv_stats": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "hpc_rll_gae_forward_ld": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
     "hpc_rll_gae_backward_ld": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
     "hpc_rll_gae_fwd_bwd_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl]),
@@ -38,6 +40,7 @@ SIGNATURES = {
     "hpc_rll_upgo_forward": (c_int, [c_vp] * 7 + [c_i64] * 4 + [c_vp, c_sz, c_vp]),
     "hpc_rll_upgo_backward": (c_int, [c_vp] * 5 + [c_i64] * 3 + [c_vp]),
     "hpc_rll_ppo_forward": (c_int, [c_vp] * 11 + [c_i64, c_i64, c_dbl, c_int, c_dbl, c_i64, c_vp, c_sz, c_vp]),
+    "hpc_rll_ppo_forward_norm": (c_int, [c_vp] * 12 + [c_i64, c_i64, c_dbl, c_int, c_dbl, c_i64, c_vp, c_sz, c_vp]),
     "hpc_rll_ppo_backward": (c_int, [c_vp] * 10 + [c_i64] * 3 + [c_vp]),
     "hpc_rll_q_nstep_td_forward": (c_int, [c_vp] * 10 + [c_i64] * 3 + [c_dbl, c_int, c_i64, c_vp, c_sz, c_vp]),
     "hpc_rll_q_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 2 + [c_vp]),
@@ -54,7 +57,7 @@ SIGNATURES = {
 }
 
 OP_GAE, OP_TD_LAMBDA, OP_VTRACE, OP_UPGO, OP_PPO, OP_Q_NSTEP_TD, OP_DIST_NSTEP_TD, OP_QRDQN_NSTEP_TD, \
-    OP_IQN_NSTEP_TD = range(9)
+    OP_IQN_NSTEP_TD, OP_GAE_MOMENTS = range(10)
 
 _lib = None
 

@@ -31,6 +31,7 @@
 #include <mutex>
 #include <vector>
 
+#include "reduce.cuh"
 #include "scan_pipe.cuh"
 
 namespace hpcrll {
@@ -105,39 +106,68 @@ __device__ __forceinline__ float div_by_table(float x, float d, float r) {
     return __fmaf_rn(__fmaf_rn(-d, q0, x), r, q0);
 }
 
+// MOM: also accumulate sum(adv) and sum(adv^2) in fp64 (hpc_rll_gae_forward_moments)
+template <bool MOM = false>
 struct GaeFwdBody {
     float g, v1, gamma, factor;
     float* adv;  // running pointer: &adv[t][col] of the NEXT step (steps arrive with t descending)
     int64_t ld;
     bool valid;
+    double m1, m2;
     __device__ __forceinline__ void step(int /*t*/, const float (&x)[2], const float (&dt)[2]) {
         // x[0] = v_t, x[1] = r_t, dt = (d_t, 1/d_t)
         const float delta = __fsub_rn(__fadd_rn(x[1], __fmul_rn(gamma, v1)), x[0]);
         g = __fadd_rn(__fmul_rn(dt[0], delta), __fmul_rn(factor, g));
-        if (valid) st_stream(adv, div_by_table(g, dt[0], dt[1]));
+        const float a = div_by_table(g, dt[0], dt[1]);
+        if (valid) st_stream(adv, a);
+        if (MOM) {
+            const double ad = static_cast<double>(a);
+            m1 += ad;
+            m2 = fma(ad, ad, m2);
+        }
         adv -= ld;
         v1 = x[0];
     }
 };
 
-template <int BT, int TT, int ST>
+// per-CTA moment partials -> partials[blockIdx.x] (sum) and partials[gridDim.x + blockIdx.x] (sum of squares)
+template <bool MOM>
+__device__ __forceinline__ void gae_store_moments(const GaeFwdBody<MOM>& body, double* __restrict__ partials,
+                                                  double* red) {
+    if (MOM) {
+        double v[2] = {body.valid ? body.m1 : 0.0, body.valid ? body.m2 : 0.0};
+        block_sum<2>(v, red);
+        if (threadIdx.x == 0) {
+            partials[blockIdx.x] = v[0];
+            partials[gridDim.x + blockIdx.x] = v[1];
+        }
+    }
+}
+
+template <int BT, int TT, int ST, bool MOM>
 __global__ void __launch_bounds__(BT + 32) gae_fwd_tma(const __grid_constant__ TmapPack<2> maps,
                                                         const float* __restrict__ dtab,
                                                         const float* __restrict__ value, int64_t ld_value,
                                                         float* __restrict__ adv, int64_t ld_adv, int T, int B,
-                                                        float gamma, float factor) {
+                                                        float gamma, float factor, double* __restrict__ partials) {
     using Pipe = ScanPipe<2, BT, TT, ST, 2>;
     const int col0 = blockIdx.x * BT;
     const int col = col0 + threadIdx.x;
-    GaeFwdBody body;
+    GaeFwdBody<MOM> body;
     body.valid = threadIdx.x < BT && col < B;
     body.g = 0.f;
     body.gamma = gamma;
     body.factor = factor;
     body.ld = ld_adv;
+    body.m1 = 0.0;
+    body.m2 = 0.0;
     body.adv = adv + static_cast<int64_t>(T - 1) * ld_adv + col;
     body.v1 = body.valid ? __ldg(value + static_cast<int64_t>(T) * ld_value + col) : 0.f;
     Pipe::template run<true>(maps, dtab, T, col0, body);
+    if constexpr (MOM) {
+        __shared__ double red[64];
+        gae_store_moments<MOM>(body, partials, red);
+    }
 }
 
 struct GaeBwdBody {
@@ -187,44 +217,54 @@ __global__ void __launch_bounds__(BT + 32) gae_bwd_tma(const __grid_constant__ T
 // Generic (no alignment requirements) variants: one thread per column, plain coalesced loads with
 // a 4-deep software prefetch.  Used when a pointer / pitch is not 16-byte aligned so TMA cannot
 // describe the tensor.  Still a CUDA kernel -- there is no CPU path.
+template <bool MOM>
 __global__ void __launch_bounds__(128) gae_fwd_generic(const float* __restrict__ value, int64_t ld_value,
                                                         const float* __restrict__ reward, int64_t ld_reward,
                                                         const float* __restrict__ dtab, float* __restrict__ adv,
-                                                        int64_t ld_adv, int T, int B, float gamma, float factor) {
+                                                        int64_t ld_adv, int T, int B, float gamma, float factor,
+                                                        double* __restrict__ partials) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= B) return;
-    GaeFwdBody body;
-    body.valid = true;
-    body.g = 0.f;
-    body.gamma = gamma;
-    body.factor = factor;
-    body.ld = ld_adv;
-    body.adv = adv + static_cast<int64_t>(T - 1) * ld_adv + col;
-    body.v1 = value[static_cast<int64_t>(T) * ld_value + col];
-    constexpr int U = 8;
-    int t = T - 1;
-    for (; t >= U - 1; t -= U) {
-        float v[U], r[U];
-        float2 d[U];
+    GaeFwdBody<MOM> body;
+    body.valid = col < B;
+    body.m1 = 0.0;
+    body.m2 = 0.0;
+    if (!MOM && !body.valid) return;
+    if (body.valid) {
+        body.g = 0.f;
+        body.gamma = gamma;
+        body.factor = factor;
+        body.ld = ld_adv;
+        body.adv = adv + static_cast<int64_t>(T - 1) * ld_adv + col;
+        body.v1 = value[static_cast<int64_t>(T) * ld_value + col];
+        constexpr int U = 8;
+        int t = T - 1;
+        for (; t >= U - 1; t -= U) {
+            float v[U], r[U];
+            float2 d[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            v[u] = ld_stream(value + static_cast<int64_t>(t - u) * ld_value + col);
-            r[u] = ld_stream(reward + static_cast<int64_t>(t - u) * ld_reward + col);
-            d[u] = __ldg(reinterpret_cast<const float2*>(dtab) + t - u);
+            for (int u = 0; u < U; ++u) {
+                v[u] = ld_stream(value + static_cast<int64_t>(t - u) * ld_value + col);
+                r[u] = ld_stream(reward + static_cast<int64_t>(t - u) * ld_reward + col);
+                d[u] = __ldg(reinterpret_cast<const float2*>(dtab) + t - u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float x[2] = {v[u], r[u]};
+                const float dt[2] = {d[u].x, d[u].y};
+                body.step(t - u, x, dt);
+            }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float x[2] = {v[u], r[u]};
-            const float dt[2] = {d[u].x, d[u].y};
-            body.step(t - u, x, dt);
+        for (; t >= 0; --t) {
+            const float x[2] = {value[static_cast<int64_t>(t) * ld_value + col],
+                                reward[static_cast<int64_t>(t) * ld_reward + col]};
+            const float2 d = __ldg(reinterpret_cast<const float2*>(dtab) + t);
+            const float dt[2] = {d.x, d.y};
+            body.step(t, x, dt);
         }
     }
-    for (; t >= 0; --t) {
-        const float x[2] = {value[static_cast<int64_t>(t) * ld_value + col],
-                            reward[static_cast<int64_t>(t) * ld_reward + col]};
-        const float2 d = __ldg(reinterpret_cast<const float2*>(dtab) + t);
-        const float dt[2] = {d.x, d.y};
-        body.step(t, x, dt);
+    if constexpr (MOM) {
+        __shared__ double red[64];
+        gae_store_moments<MOM>(body, partials, red);
     }
 }
 
@@ -309,7 +349,7 @@ __global__ void __launch_bounds__(kSplitThreads) gae_fwd_split(const float* __re
             g = fmaf(powf(factor, static_cast<float>(len_k)), g, __ldcg(agg + static_cast<int64_t>(k) * B + col));
         }
     }
-    GaeFwdBody body;
+    GaeFwdBody<> body;
     body.valid = WRITE;
     body.g = g;
     body.gamma = gamma;
@@ -406,13 +446,13 @@ __global__ void __launch_bounds__(kSplitThreads) gae_bwd_split(const float* __re
 // launchers
 // ------------------------------------------------------------------------------------------------
 
-template <int BT, int TT, int ST>
+template <int BT, int TT, int ST, bool MOM = false>
 static int launch_fwd_tma(const float* value, int64_t ldv, const float* reward, int64_t ldr, const float* dtab,
                           float* adv, int64_t lda, int64_t T, int64_t B, float gamma, float factor,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, double* partials = nullptr, int* nblocks = nullptr) {
     using Pipe = ScanPipe<2, BT, TT, ST, 2>;
     static SmemOptIn opt;
-    auto kernel = gae_fwd_tma<BT, TT, ST>;
+    auto kernel = gae_fwd_tma<BT, TT, ST, MOM>;
     if (int rc0 = opt.ensure(kernel, Pipe::kSmemBytes)) return rc0;
     TmapPack<2> maps;
     int rc = make_tmap_2d(&maps.m[0], value, T + 1, B, ldv, TT, BT);
@@ -420,8 +460,9 @@ static int launch_fwd_tma(const float* value, int64_t ldv, const float* reward, 
     rc = make_tmap_2d(&maps.m[1], reward, T, B, ldr, TT, BT);
     if (rc) return rc;
     const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
-    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, dtab, value, ldv, adv, lda,
-                                                              static_cast<int>(T), static_cast<int>(B), gamma, factor);
+    if (nblocks) *nblocks = static_cast<int>(grid);
+    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, dtab, value, ldv, adv, lda, static_cast<int>(T),
+                                                              static_cast<int>(B), gamma, factor, partials);
     count_launch();
     HPC_LAUNCH_CHECK();
     return HPC_RLL_OK;
@@ -572,8 +613,78 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
         default: break;
     }
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);
-    gae_fwd_generic<<<grid, 128, 0, stream>>>(value, ldv, reward, ldr, dtab, adv, lda, static_cast<int>(T),
-                                              static_cast<int>(B), g, f);
+    gae_fwd_generic<false><<<grid, 128, 0, stream>>>(value, ldv, reward, ldr, dtab, adv, lda, static_cast<int>(T),
+                                                     static_cast<int>(B), g, f, nullptr);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+// sum / sum-of-squares of the per-CTA partials, fixed order -> moments[0..1] (fp64)
+__global__ void __launch_bounds__(256) gae_finalize_moments(const double* __restrict__ partials, int n,
+                                                             double* __restrict__ moments) {
+    __shared__ double scratch[64];
+    double v[2] = {0.0, 0.0};
+    for (int i = threadIdx.x; i < n; i += 256) {
+        v[0] += partials[i];
+        v[1] += partials[n + i];
+    }
+    block_sum<2>(v, scratch);
+    if (threadIdx.x == 0) {
+        moments[0] = v[0];
+        moments[1] = v[1];
+    }
+}
+
+// stats[0] = mean, stats[1] = unbiased std + 1e-8 (fp32 add, as `adv.std() + 1e-8` on an fp32 tensor)
+__global__ void adv_stats_kernel(const double* __restrict__ moments, double count, float* __restrict__ stats) {
+    const double s1 = moments[0], s2 = moments[1];
+    if (count <= 0.0) count = moments[2];  // count carried (and all-reduced) next to the sums
+    const double mean = s1 / count;
+    const double var = (s2 - s1 * mean) / (count - 1.0);  // count == 1 -> NaN like torch.std
+    const float sd = static_cast<float>(sqrt(var > 0.0 ? var : (var == var ? 0.0 : var)));
+    stats[0] = static_cast<float>(mean);
+    stats[1] = __fadd_rn(sd, 1e-8f);
+}
+
+size_t gae_moments_workspace_bytes(int64_t B) { return 2 * sizeof(double) * static_cast<size_t>((B + 31) / 32 + 8); }
+
+static int gae_forward_moments_impl(const float* value, const float* reward, float* adv, double* moments, int64_t T,
+                                    int64_t B, double gamma, double lambda, double* partials, cudaStream_t stream) {
+    const float* dtab = nullptr;
+    int rc = get_dtab(T, lambda, &dtab);
+    if (rc) return rc;
+    const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
+    int cfg = pick_cfg(B);
+    if (!(tma_ok_2d(value, B, B) && tma_ok_2d(reward, B, B))) cfg = 99;
+    int nblocks = 0;
+    switch (cfg) {  // the tile shapes the automatic choice uses; anything else maps to the nearest of them
+        case 7: case 8: case 10: case 11:
+            rc = launch_fwd_tma<256, 8, 4, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
+            break;
+        case 1: case 4: case 6:
+            rc = launch_fwd_tma<128, 16, 3, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
+            break;
+        case 0: case 3: case 5:
+            rc = launch_fwd_tma<64, 16, 3, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
+            break;
+        case 2: case 14:
+            rc = launch_fwd_tma<32, 32, 3, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
+            break;
+        case 13: case 20:
+            rc = launch_fwd_tma<32, 64, 6, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
+            break;
+        default: {
+            const unsigned grid = static_cast<unsigned>((B + 127) / 128);
+            nblocks = static_cast<int>(grid);
+            gae_fwd_generic<true><<<grid, 128, 0, stream>>>(value, B, reward, B, dtab, adv, B, static_cast<int>(T),
+                                                            static_cast<int>(B), g, f, partials);
+            count_launch();
+            HPC_LAUNCH_CHECK();
+        }
+    }
+    if (rc) return rc;
+    gae_finalize_moments<<<1, 256, 0, stream>>>(partials, nblocks, moments);
     count_launch();
     HPC_LAUNCH_CHECK();
     return HPC_RLL_OK;
@@ -727,6 +838,28 @@ extern "C" {
 int hpc_rll_gae_forward(const float* value, const float* reward, float* adv, int64_t T, int64_t B, double gamma,
                         double lambda, void* stream) {
     return hpcrll::gae_forward_impl(value, B, reward, B, adv, B, T, B, gamma, lambda, hpcrll::as_stream(stream));
+}
+
+int hpc_rll_gae_forward_moments(const float* value, const float* reward, float* adv, double* moments, int64_t T,
+                                int64_t B, double gamma, double lambda, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    using namespace hpcrll;
+    HPC_REQUIRE(T > 0 && B > 0, "gae_forward_moments: T and B must be positive (T=%lld B=%lld)", (long long)T,
+                (long long)B);
+    HPC_REQUIRE(value && reward && adv && moments && workspace, "gae_forward_moments: null pointer");
+    HPC_REQUIRE(workspace_bytes >= gae_moments_workspace_bytes(B), "gae_forward_moments: workspace too small");
+    HPC_REQUIRE(T < (int64_t(1) << 31) - 64 && B < (int64_t(1) << 31) - 512, "gae_forward_moments: T/B exceed 2^31");
+    return gae_forward_moments_impl(value, reward, adv, moments, T, B, gamma, lambda, static_cast<double*>(workspace),
+                                    as_stream(stream));
+}
+
+int hpc_rll_adv_stats(const double* moments, int64_t count, float* stats, void* stream) {
+    using namespace hpcrll;
+    HPC_REQUIRE(moments && stats, "adv_stats: null pointer");
+    adv_stats_kernel<<<1, 1, 0, as_stream(stream)>>>(moments, static_cast<double>(count), stats);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
 }
 
 int hpc_rll_gae_backward(const float* grad_adv, float* grad_value, float* grad_reward, int64_t T, int64_t B,

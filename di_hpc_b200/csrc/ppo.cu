@@ -20,6 +20,15 @@ struct PpoParams {
     float lo, hi, eps, dual;  // 1-clip, 1+clip, clip, dual_clip (<=0: off)
     int use_value_clip;
     float inv_n;
+    const float* adv_stats;  // {mean, std + 1e-8} on the device, or nullptr (adv already normalised)
+};
+
+// (adv - mean) / (std + 1e-8) with the statistics of hpc_rll_adv_stats; identity when there are none
+struct AdvNorm {
+    float mean, denom;
+    __device__ __forceinline__ explicit AdvNorm(const PpoParams& P)
+        : mean(P.adv_stats ? __ldg(P.adv_stats) : 0.f), denom(P.adv_stats ? __ldg(P.adv_stats + 1) : 1.f) {}
+    __device__ __forceinline__ float operator()(float a) const { return __fdiv_rn(__fsub_rn(a, mean), denom); }
 };
 
 // scalar part for one sample; returns the five loss terms' contributions and the two coefficients
@@ -83,6 +92,7 @@ __global__ void __launch_bounds__(256, KMAX >= 8 ? 1 : 3) ppo_rows_fwd(const flo
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
     double acc[5] = {0, 0, 0, 0, 0};
+    const AdvNorm norm(P);
     constexpr bool PF = KMAX <= 2;  // software pipeline (see softmax_rows.cu)
     Row rn, ro, nn, no;
     int a, na = -1;
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(256, KMAX >= 8 ? 1 : 3) ppo_rows_fwd(const flo
         const float selo = row_logp<true>(group_sum(ro.select(a, G, lig), G), mo, lso);
         if (active && lig == 0) {
             float pc, vc;
-            ppo_sample(P, seln, selo, H, adv[row], value_new[row], value_old[row], ret[row],
+            ppo_sample(P, seln, selo, H, norm(adv[row]), value_new[row], value_old[row], ret[row],
                        weight ? weight[row] : 1.f, acc, pc, vc);
             pol_coef[row] = pc;
             val_coef[row] = vc;
@@ -145,6 +155,7 @@ __global__ void __launch_bounds__(kStageRows) ppo_rows_fwd_staged(
     float* tn = tiles;
     float* to = tiles + kStageRows * pitch;
     double acc[5] = {0, 0, 0, 0, 0};
+    const AdvNorm norm(P);
     const int64_t ntiles = (R + kStageRows - 1) / kStageRows;
     for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
         const int64_t row0 = tix * kStageRows, row = row0 + threadIdx.x;
@@ -162,8 +173,8 @@ __global__ void __launch_bounds__(kStageRows) ppo_rows_fwd_staged(
             const float H = lsn - t1 / sn;
             const int a = static_cast<int>(action[row]);
             float pc, vc;
-            ppo_sample(P, row_logp<true>(xn[a], mn, lsn), row_logp<true>(xo[a], mo, lso), H, adv[row], value_new[row],
-                       value_old[row], ret[row], weight ? weight[row] : 1.f, acc, pc, vc);
+            ppo_sample(P, row_logp<true>(xn[a], mn, lsn), row_logp<true>(xo[a], mo, lso), H, norm(adv[row]),
+                       value_new[row], value_old[row], ret[row], weight ? weight[row] : 1.f, acc, pc, vc);
             pol_coef[row] = pc;
             val_coef[row] = vc;
         }
@@ -188,6 +199,7 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd_loop(const float* __restrict
     __shared__ double red[5 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double acc[5] = {0, 0, 0, 0, 0};
+    const AdvNorm norm(P);
     for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < R; row += static_cast<int64_t>(gridDim.x) * 8) {
         const float* xn = logits_new + row * N;
         const float* xo = logits_old + row * N;
@@ -215,8 +227,8 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd_loop(const float* __restrict
         if (lane == 0) {
             const int a = static_cast<int>(action[row]);
             float pc, vc;
-            ppo_sample(P, row_logp<true>(xn[a], mn, lsn), row_logp<true>(xo[a], mo, lso), H, adv[row], value_new[row],
-                       value_old[row], ret[row], weight ? weight[row] : 1.f, acc, pc, vc);
+            ppo_sample(P, row_logp<true>(xn[a], mn, lsn), row_logp<true>(xo[a], mo, lso), H, norm(adv[row]),
+                       value_new[row], value_old[row], ret[row], weight ? weight[row] : 1.f, acc, pc, vc);
             pol_coef[row] = pc;
             val_coef[row] = vc;
         }
@@ -230,16 +242,12 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd_loop(const float* __restrict
 
 size_t ppo_workspace_bytes() { return static_cast<size_t>(sm_count()) * 16 * 5 * 8 + 256; }
 
-}  // namespace hpcrll
-
-extern "C" {
-
-int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const int64_t* action,
-                        const float* value_new, const float* value_old, const float* adv, const float* return_,
-                        const float* weight, float* out5, float* pol_coef, float* val_coef, int64_t B, int64_t N,
-                        double clip_ratio, int use_value_clip, double dual_clip, int64_t global_B, void* workspace,
-                        size_t workspace_bytes, void* stream_) {
-    using namespace hpcrll;
+static int ppo_forward_impl(const float* logits_new, const float* logits_old, const int64_t* action,
+                            const float* value_new, const float* value_old, const float* adv, const float* return_,
+                            const float* weight, const float* adv_stats, float* out5, float* pol_coef,
+                            float* val_coef, int64_t B, int64_t N, double clip_ratio, int use_value_clip,
+                            double dual_clip, int64_t global_B, void* workspace, size_t workspace_bytes,
+                            void* stream_) {
     cudaStream_t stream = as_stream(stream_);
     HPC_REQUIRE(B > 0 && N > 0, "ppo_forward: sizes must be positive (B=%lld N=%lld)", (long long)B, (long long)N);
     HPC_REQUIRE(logits_new && logits_old && action && value_new && value_old && adv && return_ && out5 && pol_coef &&
@@ -257,6 +265,7 @@ int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const 
     P.dual = dual_clip > 0.0 ? static_cast<float>(dual_clip) : 0.f;
     P.use_value_clip = use_value_clip;
     P.inv_n = static_cast<float>(inv_n);
+    P.adv_stats = adv_stats;
     double* partials = static_cast<double*>(workspace);
     const RowGeom ge = row_geom(N, aligned16(logits_new) && aligned16(logits_old));
     int log2G = 0;
@@ -289,6 +298,33 @@ int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const 
         spec.scale[k] = sc[k];
     }
     return launch_finalize_terms(partials, spec, 5, out5, stream);
+}
+
+}  // namespace hpcrll
+
+extern "C" {
+
+int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const int64_t* action,
+                        const float* value_new, const float* value_old, const float* adv, const float* return_,
+                        const float* weight, float* out5, float* pol_coef, float* val_coef, int64_t B, int64_t N,
+                        double clip_ratio, int use_value_clip, double dual_clip, int64_t global_B, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    return hpcrll::ppo_forward_impl(logits_new, logits_old, action, value_new, value_old, adv, return_, weight, nullptr,
+                                    out5, pol_coef, val_coef, B, N, clip_ratio, use_value_clip, dual_clip, global_B,
+                                    workspace, workspace_bytes, stream);
+}
+
+int hpc_rll_ppo_forward_norm(const float* logits_new, const float* logits_old, const int64_t* action,
+                             const float* value_new, const float* value_old, const float* adv, const float* return_,
+                             const float* weight, const float* adv_stats, float* out5, float* pol_coef,
+                             float* val_coef, int64_t B, int64_t N, double clip_ratio, int use_value_clip,
+                             double dual_clip, int64_t global_B, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    using namespace hpcrll;
+    HPC_REQUIRE(adv_stats, "ppo_forward_norm: adv_stats is null (use hpc_rll_ppo_forward for pre-normalised adv)");
+    return ppo_forward_impl(logits_new, logits_old, action, value_new, value_old, adv, return_, weight, adv_stats, out5,
+                            pol_coef, val_coef, B, N, clip_ratio, use_value_clip, dual_clip, global_B, workspace,
+                            workspace_bytes, stream);
 }
 
 int hpc_rll_ppo_backward(const float* grad_policy_loss, const float* grad_value_loss, const float* grad_entropy_loss,

@@ -5,6 +5,7 @@
 namespace hpcrll {
 
 size_t td_lambda_workspace_bytes(int64_t B);
+size_t gae_moments_workspace_bytes(int64_t B);
 size_t vtrace_workspace_bytes(int64_t T, int64_t B);
 size_t upgo_workspace_bytes(int64_t T, int64_t B);
 size_t ppo_workspace_bytes();
@@ -17,6 +18,8 @@ size_t workspace_bytes(int op, int64_t T, int64_t B, int64_t N) {
     switch (op) {
         case HPC_RLL_OP_GAE:
             return 0;
+        case HPC_RLL_OP_GAE_MOMENTS:
+            return gae_moments_workspace_bytes(B);
         case HPC_RLL_OP_TD_LAMBDA:
             return td_lambda_workspace_bytes(B);
         case HPC_RLL_OP_VTRACE:

@@ -44,6 +44,48 @@ class GAEFunction(torch.autograd.Function):
         return grad_value, grad_reward, None, None
 
 
+def gae_with_adv_stats(value, reward, gamma: float = 0.99, lambda_: float = 0.97, group=None):
+    """
+    Overview:
+        GAE forward fused with the statistics of the advantage normalisation
+        ``(adv - adv.mean()) / (adv.std() + 1e-8)`` that precedes ``ppo_error``
+        (hpc_rll/origin/ppo.py:43-47): the scan kernel accumulates sum(adv) and sum(adv^2) in fp64 while it
+        writes ``adv``, so mean/std cost no extra pass over HBM.  Hand ``adv_stats`` to ``PPO.forward(...,
+        adv_stats=adv_stats)`` and the normalisation itself happens inside the PPO kernel.  No autograd
+        (advantages are targets; the reference's GAE has no backward at all, rl_utils/gae.py:16-18).
+    Arguments:
+        - value (:obj:`torch.FloatTensor`): :math:`(T + 1, B)`; reward :math:`(T, B)`
+        - group: ``torch.distributed`` group over which the batch axis is sharded (moments are all-reduced)
+    Returns:
+        - adv (:obj:`torch.FloatTensor`): :math:`(T, B)`, NOT normalised
+        - adv_stats (:obj:`torch.FloatTensor`): :math:`(2,)` = ``[mean, std + 1e-8]`` of the (global) advantages
+    """
+    from ..sharding import all_reduce_moments
+    value = _abi.require_f32_cuda("value", value.detach())
+    reward = _abi.require_f32_cuda("reward", reward.detach())
+    T, B = reward.shape
+    if value.shape != (T + 1, B):
+        raise ValueError("value must be (T+1, B)=(%d, %d), got %s" % (T + 1, B, tuple(value.shape)))
+    if T == 0 or B == 0:
+        raise ValueError("gae_with_adv_stats needs a non-empty batch")
+    dev = reward.device
+    adv = torch.empty_like(reward)
+    moments = torch.empty(3, dtype=torch.float64, device=dev)
+    moments[2] = T * B
+    stats = torch.empty(2, dtype=torch.float32, device=dev)
+    ws = _abi.workspace(_abi.OP_GAE_MOMENTS, T, B, 0, dev)
+    with _abi.on_device(dev):
+        _abi.check(
+            _abi.lib().hpc_rll_gae_forward_moments(_abi.ptr(value), _abi.ptr(reward), _abi.ptr(adv),
+                                                   _abi.ptr(moments), T, B, float(gamma), float(lambda_),
+                                                   _abi.ptr(ws), ws.numel(), _abi.stream_of(reward)),
+            "hpc_rll_gae_forward_moments")
+        all_reduce_moments(moments, group)
+        _abi.check(_abi.lib().hpc_rll_adv_stats(_abi.ptr(moments), 0, _abi.ptr(stats), _abi.stream_of(reward)),
+                   "hpc_rll_adv_stats")
+    return adv, stats
+
+
 class GAE(torch.nn.Module):
     """
     Overview:

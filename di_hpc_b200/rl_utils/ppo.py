@@ -17,7 +17,7 @@ class PPOFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, logits_new, logits_old, action, value_new, value_old, adv, return_, weight, clip_ratio,
-                use_value_clip, dual_clip, global_B):
+                use_value_clip, dual_clip, global_B, adv_stats=None):
         logits_new = _abi.require_f32_cuda("logits_new", logits_new)
         logits_old = _abi.require_f32_cuda("logits_old", logits_old)
         action = _abi.require_i64_cuda("action", action)
@@ -32,20 +32,26 @@ class PPOFunction(torch.autograd.Function):
             weight = _abi.require_f32_cuda("weight", weight)
             if weight.shape != (B, ):
                 raise ValueError("weight must be (B,)")
+        if adv_stats is not None:
+            adv_stats = _abi.require_f32_cuda("adv_stats", adv_stats)
+            if adv_stats.shape != (2, ):
+                raise ValueError("adv_stats must be (2,) = [mean, std + 1e-8]")
         dev = adv.device
         out = torch.empty(5, dtype=torch.float32, device=dev)
         pol_coef = torch.empty(B, dtype=torch.float32, device=dev)
         val_coef = torch.empty(B, dtype=torch.float32, device=dev)
         ws = _abi.workspace(_abi.OP_PPO, 0, B, N, dev)
+        tail = (_abi.ptr(out), _abi.ptr(pol_coef), _abi.ptr(val_coef), B, N, float(clip_ratio),
+                1 if use_value_clip else 0, -1.0 if dual_clip is None else float(dual_clip), int(global_B),
+                _abi.ptr(ws), ws.numel(), _abi.stream_of(adv))
+        head = (_abi.ptr(logits_new), _abi.ptr(logits_old), _abi.ptr(action), _abi.ptr(value_new),
+                _abi.ptr(value_old), _abi.ptr(adv), _abi.ptr(return_), _abi.ptr(weight))
         with _abi.on_device(dev):
-            _abi.check(
-                _abi.lib().hpc_rll_ppo_forward(_abi.ptr(logits_new), _abi.ptr(logits_old), _abi.ptr(action),
-                                               _abi.ptr(value_new), _abi.ptr(value_old), _abi.ptr(adv),
-                                               _abi.ptr(return_), _abi.ptr(weight), _abi.ptr(out), _abi.ptr(pol_coef),
-                                               _abi.ptr(val_coef), B, N, float(clip_ratio),
-                                               1 if use_value_clip else 0,
-                                               -1.0 if dual_clip is None else float(dual_clip), int(global_B),
-                                               _abi.ptr(ws), ws.numel(), _abi.stream_of(adv)), "hpc_rll_ppo_forward")
+            if adv_stats is None:
+                _abi.check(_abi.lib().hpc_rll_ppo_forward(*head, *tail), "hpc_rll_ppo_forward")
+            else:
+                _abi.check(_abi.lib().hpc_rll_ppo_forward_norm(*head, _abi.ptr(adv_stats), *tail),
+                           "hpc_rll_ppo_forward_norm")
         ctx.save_for_backward(logits_new, action, weight, pol_coef, val_coef)
         ctx.global_B = int(global_B)
         info = out[3:5]
@@ -67,7 +73,7 @@ class PPOFunction(torch.autograd.Function):
                                                 _abi.ptr(action), _abi.ptr(weight), _abi.ptr(pol_coef),
                                                 _abi.ptr(val_coef), _abi.ptr(grad_logits), _abi.ptr(grad_value), B, N,
                                                 ctx.global_B, _abi.stream_of(pol_coef)), "hpc_rll_ppo_backward")
-        return grad_logits, None, None, grad_value, None, None, None, None, None, None, None, None
+        return grad_logits, None, None, grad_value, None, None, None, None, None, None, None, None, None
 
 
 class PPO(torch.nn.Module):
@@ -90,7 +96,8 @@ class PPO(torch.nn.Module):
         self.global_B = 0
 
     def forward(self, logits_new, logits_old, action, value_new, value_old, adv, return_, weight=None,
-                clip_ratio: float = 0.2, use_value_clip: bool = True, dual_clip: Optional[float] = None):
+                clip_ratio: float = 0.2, use_value_clip: bool = True, dual_clip: Optional[float] = None,
+                *, adv_stats: Optional[torch.Tensor] = None):
         """
         Arguments:
             - logits_new, logits_old (:obj:`torch.FloatTensor`): :math:`(B, N)`
@@ -100,6 +107,9 @@ class PPO(torch.nn.Module):
             - clip_ratio (:obj:`float`): defaults to 0.2
             - use_value_clip (:obj:`bool`)
             - dual_clip (:obj:`float` or None): must be > 1.0 when given
+            - adv_stats (:obj:`torch.FloatTensor` or None): extension -- :math:`(2,)` ``[mean, std + 1e-8]`` from
+              ``gae_with_adv_stats``; ``adv`` is then normalised inside the kernel (origin/ppo.py:43-47 leaves
+              that step to the caller)
         Returns:
             - ppo_loss (:obj:`hpc_ppo_loss`): shape-(1,) tensors
             - ppo_info (:obj:`hpc_ppo_info`): Python floats
@@ -117,6 +127,7 @@ class PPO(torch.nn.Module):
             "dual_clip value must be greater than 1.0, but get value: {}".format(dual_clip)
         policy_loss, value_loss, entropy_loss, info = PPOFunction.apply(logits_new, logits_old, action, value_new,
                                                                         value_old, adv, return_, weight, clip_ratio,
-                                                                        use_value_clip, dual_clip, self.global_B)
+                                                                        use_value_clip, dual_clip, self.global_B,
+                                                                        adv_stats)
         approx_kl, clipfrac = info.tolist()  # one device->host copy
         return hpc_ppo_loss(policy_loss, value_loss, entropy_loss), hpc_ppo_info(approx_kl, clipfrac)

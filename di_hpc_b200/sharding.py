@@ -63,6 +63,17 @@ def all_reduce_losses(losses: Sequence[torch.Tensor], group=None):
     return out
 
 
+def all_reduce_moments(moments: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place all-reduce(SUM) of ``[sum(adv), sum(adv^2), count]`` (fp64) over the ranks that shard the
+    batch: the element count rides in the same tensor, so the global mean/std need one latency-bound
+    collective and no device->host read."""
+    if moments.dtype != torch.float64 or moments.numel() != 3:
+        raise TypeError("moments must be 3 float64 values [sum, sum of squares, count]")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(moments, op=dist.ReduceOp.SUM, group=group)
+    return moments
+
+
 def set_global_batch(module: torch.nn.Module, global_B: int) -> torch.nn.Module:
     """Tell a loss module that its batch is one shard of ``global_B`` columns/samples."""
     if not hasattr(module, "global_B"):

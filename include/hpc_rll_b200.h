@@ -46,7 +46,8 @@ extern "C" {
 #define HPC_RLL_OP_DIST_NSTEP_TD 6
 #define HPC_RLL_OP_QRDQN_NSTEP_TD 7
 #define HPC_RLL_OP_IQN_NSTEP_TD 8
-#define HPC_RLL_OP_COUNT 9
+#define HPC_RLL_OP_GAE_MOMENTS 9 /* workspace sizing only; tuning follows HPC_RLL_OP_GAE */
+#define HPC_RLL_OP_COUNT 10
 
 /* ---- library ------------------------------------------------------------------------------ */
 const char* hpc_rll_version(void);
@@ -75,6 +76,20 @@ int hpc_rll_gae_forward_ld(const float* value, int64_t ld_value, const float* re
 int hpc_rll_gae_backward_ld(const float* grad_adv, int64_t ld_grad_adv, float* grad_value, int64_t ld_grad_value,
                             float* grad_reward, int64_t ld_grad_reward, int64_t T, int64_t B, double gamma,
                             double lambda, void* stream);
+/* GAE forward that also returns the raw moments of the advantages it writes:
+ *   moments[0] = sum(adv), moments[1] = sum(adv^2)   (fp64, device memory, fixed summation order)
+ * for the normalisation (adv - adv.mean()) / (adv.std() + 1e-8) that precedes ppo_error
+ * (/root/reference/hpc_rll/origin/ppo.py:43-47) -- fused here so that `adv` is not re-read twice for
+ * mean and std.  Data-parallel callers all-reduce(SUM) `moments` before hpc_rll_adv_stats.
+ * value/reward/adv contiguous.  Workspace: hpc_rll_workspace_bytes(HPC_RLL_OP_GAE_MOMENTS, T, B, 0). */
+int hpc_rll_gae_forward_moments(const float* value, const float* reward, float* adv, double* moments, int64_t T,
+                                int64_t B, double gamma, double lambda, void* workspace, size_t workspace_bytes,
+                                void* stream);
+/* moments (device, fp64) over `count` elements -> stats[0] = mean, stats[1] = unbiased std + 1e-8
+ * (device, fp32; exactly the two scalars of the normalisation above).  count == 1 gives NaN like torch.std.
+ * count <= 0: the element count is read from moments[2] (a caller-filled third double, so that sums and
+ * count travel through one all-reduce and no host round trip is needed). */
+int hpc_rll_adv_stats(const double* moments, int64_t count, float* stats, void* stream);
 /* HOST-buffer entry (end-to-end path): pinned or pageable host arrays in, host arrays out.  Runs
  * forward and backward on the current device, pipelining column blocks over H2D copy / kernels /
  * D2H copy on internal streams; returns after all results have landed in the host buffers.
@@ -139,6 +154,15 @@ int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const 
                         const float* weight, float* out5, float* pol_coef, float* val_coef, int64_t B, int64_t N,
                         double clip_ratio, int use_value_clip, double dual_clip, int64_t global_B, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* same, with the advantage normalisation fused in: every sample uses (adv - adv_stats[0]) / adv_stats[1],
+ * adv_stats = {mean, std + 1e-8} on the device as written by hpc_rll_adv_stats (origin/ppo.py:43-47 leaves
+ * this step to the caller; doing it here saves a read+write of `adv`).  Backward is unchanged. */
+int hpc_rll_ppo_forward_norm(const float* logits_new, const float* logits_old, const int64_t* action,
+                             const float* value_new, const float* value_old, const float* adv, const float* return_,
+                             const float* weight, const float* adv_stats, float* out5, float* pol_coef,
+                             float* val_coef, int64_t B, int64_t N, double clip_ratio, int use_value_clip,
+                             double dual_clip, int64_t global_B, void* workspace, size_t workspace_bytes,
+                             void* stream);
 int hpc_rll_ppo_backward(const float* grad_policy_loss, const float* grad_value_loss, const float* grad_entropy_loss,
                          const float* logits_new, const int64_t* action, const float* weight, const float* pol_coef,
                          const float* val_coef, float* grad_logits_new, float* grad_value_new, int64_t B, int64_t N,

@@ -176,6 +176,38 @@ def ppo(logits_new, logits_old, action, value_new, value_old, adv, return_, weig
                 grad_logits_new=gl, grad_value_new=gv)
 
 
+# ------------------------------------------------------------------------------------------- gae -> normalise -> ppo
+def adv_stats(adv):
+    """[mean, std + 1e-8] of the advantage normalisation described at hpc_rll/origin/ppo.py:43-47
+    (``(adv - adv.mean()) / (adv.std() + 1e-8)``; torch.std is the unbiased estimator).  Moments are
+    taken in fp64 and rounded once to the input dtype; the epsilon is added in the input dtype."""
+    dt = adv.dtype
+    a = np.asarray(adv, dtype=np.float64).reshape(-1)
+    n = a.size
+    s1, s2 = a.sum(), np.square(a).sum()
+    mean = s1 / n
+    var = (s2 - s1 * mean) / (n - 1) if n > 1 else np.nan
+    sd = np.sqrt(max(var, 0.0)) if var == var else np.nan
+    return np.array([mean, dt.type(sd) + dt.type(1e-8)], dtype=dt)
+
+
+def normalize_adv(adv, stats):
+    """(adv - mean) / (std + 1e-8), one subtraction and one IEEE division per element in adv's dtype."""
+    return ((adv - stats[0]) / stats[1]).astype(adv.dtype)
+
+
+def gae_norm_ppo(value, reward, logits_new, logits_old, action, value_new, value_old, return_, weight=None,
+                 gamma=0.99, lambda_=0.97, clip_ratio=0.2, use_value_clip=True, dual_clip=None, coef=None):
+    """SURVEY.md 8(f)3 chain: origin.gae (gae.py:28-37) -> normalisation (ppo.py:43-47) -> origin.ppo_error
+    (ppo.py:51-80) on the flattened (T*B,) batch."""
+    adv = gae_forward(value, reward, gamma, lambda_)
+    st = adv_stats(adv)
+    r = ppo(logits_new, logits_old, action, value_new, value_old, normalize_adv(adv, st).reshape(-1), return_, weight,
+            clip_ratio, use_value_clip, dual_clip, coef)
+    r["adv"], r["adv_mean"], r["adv_denom"] = adv, st[0], st[1]
+    return r
+
+
 # ------------------------------------------------------------------------------------------- n-step family
 def q_nstep_td(q, next_n_q, action, next_n_action, reward, done, weight=None, gamma=0.99, rescale=False,
                coef_loss=1.0, want_grad=True):

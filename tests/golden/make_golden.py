@@ -176,6 +176,40 @@ def case_ppo(name, B, N, use_weight, clip_ratio, use_value_clip, dual_clip, seed
                    coef_policy=coef[0], coef_value=coef[1], coef_entropy=coef[2]))
 
 
+# ----------------------------------------------------------------------------- gae -> normalise -> ppo
+def case_gae_ppo(name, T, B, N, use_weight, clip_ratio, use_value_clip, dual_clip, seed):
+    """The chain SURVEY.md 8(f)3 names: origin.gae -> (adv - mean) / (std + 1e-8) (the normalisation
+    origin/ppo.py:43-47 describes) -> origin.ppo_error on the flattened (T*B,) batch."""
+    g = gen(seed)
+    R = T * B
+    logit_old = torch.randn(R, N, generator=g)
+    inputs = dict(value=torch.randn(T + 1, B, generator=g), reward=torch.randn(T, B, generator=g),
+                  logits_new=logit_old + 0.3 * torch.randn(R, N, generator=g), logits_old=logit_old,
+                  action=torch.randint(0, N, (R,), generator=g),
+                  value_new=torch.randn(R, generator=g), value_old=torch.randn(R, generator=g),
+                  return_=torch.randn(R, generator=g),
+                  weight=torch.rand(R, generator=g) if use_weight else None)
+    coef = (1.0, 0.5, -0.01)
+    gamma, lam = 0.99, 0.97
+
+    def fn(c):
+        with torch.no_grad():
+            adv = O.gae.gae(O.gae.gae_data(c["value"], c["reward"]), gamma, lam)
+            mean, denom = adv.mean(), adv.std() + 1e-8
+            advn = ((adv - mean) / denom).reshape(-1)
+        l, info = O.ppo.ppo_error(O.ppo.ppo_data(c["logits_new"], c["logits_old"], c["action"], c["value_new"],
+                                                 c["value_old"], advn, c["return_"], c["weight"]),
+                                  clip_ratio, use_value_clip, dual_clip)
+        outs = dict(adv=adv, adv_mean=mean, adv_denom=denom, policy_loss=l.policy_loss, value_loss=l.value_loss,
+                    entropy_loss=l.entropy_loss, approx_kl=torch.tensor(info.approx_kl),
+                    clipfrac=torch.tensor(info.clipfrac))
+        return outs, coef[0] * l.policy_loss + coef[1] * l.value_loss + coef[2] * l.entropy_loss
+
+    save_case(name, fn, inputs, ["logits_new", "value_new"],
+              dict(gamma=gamma, lambda_=lam, clip_ratio=clip_ratio, use_value_clip=float(use_value_clip),
+                   dual_clip=dual_clip, coef_policy=coef[0], coef_value=coef[1], coef_entropy=coef[2]))
+
+
 # ----------------------------------------------------------------------------- q n-step (+rescale)
 def _nstep_inputs(g, T, B, N, use_weight):
     return dict(q=torch.randn(B, N, generator=g), next_n_q=torch.randn(B, N, generator=g),
@@ -283,10 +317,20 @@ def case_padding(name, ndim, n, lo_hi, value, group, seed):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
 
 
+def main_gae_ppo():
+    s = 1234
+    case_gae_ppo("gaeppo_t16_b8_n6", 16, 8, 6, False, 0.2, True, None, s + 100)
+    case_gae_ppo("gaeppo_t12_b5_n16_w_dual", 12, 5, 16, True, 0.2, True, 3.0, s + 101)
+    case_gae_ppo("gaeppo_t7_b3_n18_w", 7, 3, 18, True, 0.1, False, None, s + 102)
+
+
 def main():
+    if sys.argv[1:] == ["gaeppo"]:  # add the chain fixtures without re-zipping the others
+        return main_gae_ppo()
     for f in os.listdir(HERE):
         if f.endswith(".npz"):
             os.remove(os.path.join(HERE, f))
+    main_gae_ppo()
     s = 1234
     case_gae("gae_t16_b8", 16, 8, 0.99, 0.97, s + 1)
     case_gae("gae_t1_b5", 1, 5, 0.99, 0.97, s + 2)

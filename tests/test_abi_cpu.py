@@ -87,8 +87,12 @@ def test_reference_api_surface():
                                              "weight", "gamma", "lambda_", "rho_clip_ratio", "c_clip_ratio",
                                              "rho_pg_clip_ratio"]
     assert params(ppo.PPO.__init__) == ["B", "N"]
-    assert params(ppo.PPO.forward) == ["logits_new", "logits_old", "action", "value_new", "value_old", "adv",
-                                       "return_", "weight", "clip_ratio", "use_value_clip", "dual_clip"]
+    assert params(ppo.PPO.forward)[:11] == ["logits_new", "logits_old", "action", "value_new", "value_old", "adv",
+                                            "return_", "weight", "clip_ratio", "use_value_clip", "dual_clip"]
+    # the one extension (fused advantage normalisation) is keyword-only and off by default
+    extra = [p for p in inspect.signature(ppo.PPO.forward).parameters.values() if p.name not in
+             params(ppo.PPO.forward)[:11] and p.name != "self"]
+    assert [(p.name, p.kind, p.default) for p in extra] == [("adv_stats", inspect.Parameter.KEYWORD_ONLY, None)]
     assert vtrace.hpc_vtrace_loss._fields == ("policy_loss", "value_loss", "entropy_loss")
     assert ppo.hpc_ppo_loss._fields == ("policy_loss", "value_loss", "entropy_loss")
     assert ppo.hpc_ppo_info._fields == ("approx_kl", "clipfrac")

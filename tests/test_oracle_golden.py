@@ -88,6 +88,26 @@ def test_ppo(name, prec):
 
 
 @pytest.mark.parametrize("prec", [32, 64])
+@pytest.mark.parametrize("name", names("gaeppo"))
+def test_gae_norm_ppo_chain(name, prec):
+    """origin.gae -> (adv - mean) / (std + 1e-8) -> origin.ppo_error."""
+    c = Case(name)
+    dt = DT[prec]
+    coef = [c.attr("coef_policy"), c.attr("coef_value"), c.attr("coef_entropy")]
+    r = orc.gae_norm_ppo(c.inp("value", dt), c.inp("reward", dt), c.inp("logits_new", dt), c.inp("logits_old", dt),
+                         c.inp("action"), c.inp("value_new", dt), c.inp("value_old", dt), c.inp("return_", dt),
+                         c.inp("weight", dt), c.attr("gamma"), c.attr("lambda_"), c.attr("clip_ratio"),
+                         bool(c.attr("use_value_clip")), c.attr("dual_clip"), coef)
+    check(r["adv"], c.out("adv", prec), prec, "adv")
+    check(r["adv_mean"], c.out("adv_mean", prec), prec, "adv_mean")
+    check(r["adv_denom"], c.out("adv_denom", prec), prec, "adv_denom")
+    for k in ("policy_loss", "value_loss", "entropy_loss", "approx_kl", "clipfrac"):
+        check(r[k], c.out(k, prec), 32 if k in ("approx_kl", "clipfrac") else prec, k)
+    check(r["grad_logits_new"], c.grad("logits_new", prec), prec, "grad_logits_new")
+    check(r["grad_value_new"], c.grad("value_new", prec), prec, "grad_value_new")
+
+
+@pytest.mark.parametrize("prec", [32, 64])
 @pytest.mark.parametrize("name", names("qnstep"))
 def test_q_nstep(name, prec):
     c = Case(name)

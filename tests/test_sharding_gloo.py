@@ -28,7 +28,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from di_hpc_b200.sharding import all_reduce_losses, shard_columns
+        from di_hpc_b200.sharding import all_reduce_losses, all_reduce_moments, shard_columns
         from oracle import oracle as orc
         T, B = 12, 37
         g = np.random.default_rng(7)
@@ -49,7 +49,15 @@ def _worker(rank, world, port, q):
         want = float((value[:-1] ** 2).mean())
         ok_loss = abs(float(glob.item()) - want) < 1e-6
         ok_grad = np.allclose(x.grad.numpy(), 2 * value[:-1, b0:b1] / (T * B), atol=1e-7)
-        q.put((rank, ok_gae, ok_loss, ok_grad, (b0, b1)))
+        # advantage moments [sum, sum sq, count] of the shards all-reduce to the whole batch's statistics
+        a64 = adv_local.astype(np.float64)
+        mom = torch.tensor([a64.sum(), np.square(a64).sum(), float(a64.size)], dtype=torch.float64)
+        all_reduce_moments(mom)
+        s1, s2, n = mom.tolist()
+        mean, sd = s1 / n, np.sqrt((s2 - s1 * s1 / n) / (n - 1))
+        want_st = orc.adv_stats(orc.gae_forward(value, reward))
+        ok_mom = n == T * B and abs(mean - want_st[0]) < 1e-6 and abs(sd + 1e-8 - want_st[1]) < 1e-6
+        q.put((rank, ok_gae, ok_loss and ok_mom, ok_grad, (b0, b1)))
     finally:
         dist.destroy_process_group()
 

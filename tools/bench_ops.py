@@ -122,6 +122,36 @@ def bench_ppo(B, N, iters):
                 bwd_ms=b, launches=L)
 
 
+def bench_chain(T, B, N, iters, fused):
+    """GAE -> (adv - mean) / (std + 1e-8) -> PPO on the flattened (T*B,) batch.  fused: moments
+    ride in the GAE scan and the normalisation happens inside the PPO kernel; unfused: same kernels with the
+    normalisation done by three PyTorch passes over adv (mean, std, normalise)."""
+    from hpc_rll.rl_utils.gae import gae_with_adv_stats
+    R = T * B
+    v, r = rnd(T + 1, B), rnd(T, B)
+    lo = rnd(R, N)
+    ln = (lo + 0.3 * rnd(R, N)).requires_grad_(True)
+    a = torch.randint(0, N, (R, ), device=DEV)
+    vn = rnd(R).requires_grad_(True)
+    vo, ret = rnd(R), rnd(R)
+    g, m = GAE(T, B), PPO(R, N)
+
+    def fwd():
+        if fused:
+            adv, st = gae_with_adv_stats(v, r)
+            l, _ = m(ln, lo, a, vn, vo, adv.reshape(-1), ret, adv_stats=st)
+        else:
+            with torch.no_grad():
+                adv = g(v, r)
+                adv = ((adv - adv.mean()) / (adv.std() + 1e-8)).reshape(-1)
+            l, _ = m(ln, lo, a, vn, vo, adv, ret)
+        return l.policy_loss + l.value_loss + l.entropy_loss
+
+    f, b, L = timed(fwd, lambda o: torch.autograd.grad(o, [ln, vn], grad_outputs=ONE), iters)
+    return dict(op="gae_norm_ppo_" + ("fused" if fused else "unfused"), shape=dict(T=T, B=B, N=N), units=R,
+                unit="steps", alg_bytes=(12 + 16 * N + 50) * R, fwd_ms=f, bwd_ms=b, launches=L)
+
+
 def nstep_common(T, B, N):
     return (torch.randint(0, N, (B, ), device=DEV), torch.randint(0, N, (B, ), device=DEV), rnd(T, B),
             (torch.rand(B, device=DEV) < 0.1).float())
@@ -198,6 +228,8 @@ def main():
         ("upgo", lambda: bench_upgo(512, 32768, 16, it)),
         ("upgo128", lambda: bench_upgo(512, 4096, 128, it)),
         ("ppo", lambda: bench_ppo(1 << 22, 16, it)),
+        ("chain", lambda: bench_chain(1024, 16384, 16, it, True)),
+        ("chain_unfused", lambda: bench_chain(1024, 16384, 16, it, False)),
         ("q", lambda: bench_q(5, 1 << 22, 8, it)),
         ("q_rescale", lambda: bench_q(5, 1 << 22, 8, it, rescale=True)),
         ("dist", lambda: bench_dist(5, 1 << 18, 8, 51, it)),
