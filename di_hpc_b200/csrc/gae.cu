@@ -114,16 +114,22 @@ struct GaeFwdBody {
     int64_t ld;
     bool valid;
     double m1, m2;
-    __device__ __forceinline__ void step(int /*t*/, const float (&x)[2], const float (&dt)[2]) {
+    float p1, p2;  // fp32 partial moments of the current 16-row run, folded into m1/m2 at t % 16 == 0
+    __device__ __forceinline__ void step(int t, const float (&x)[2], const float (&dt)[2]) {
         // x[0] = v_t, x[1] = r_t, dt = (d_t, 1/d_t)
         const float delta = __fsub_rn(__fadd_rn(x[1], __fmul_rn(gamma, v1)), x[0]);
         g = __fadd_rn(__fmul_rn(dt[0], delta), __fmul_rn(factor, g));
         const float a = div_by_table(g, dt[0], dt[1]);
         if (valid) st_stream(adv, a);
-        if (MOM) {
-            const double ad = static_cast<double>(a);
-            m1 += ad;
-            m2 = fma(ad, ad, m2);
+        if (MOM) {  // t descends to 0, so the last run is always flushed
+            p1 += a;
+            p2 = fmaf(a, a, p2);
+            if ((t & 15) == 0) {
+                m1 += static_cast<double>(p1);
+                m2 += static_cast<double>(p2);
+                p1 = 0.f;
+                p2 = 0.f;
+            }
         }
         adv -= ld;
         v1 = x[0];
@@ -161,6 +167,8 @@ __global__ void __launch_bounds__(BT + 32) gae_fwd_tma(const __grid_constant__ T
     body.ld = ld_adv;
     body.m1 = 0.0;
     body.m2 = 0.0;
+    body.p1 = 0.f;
+    body.p2 = 0.f;
     body.adv = adv + static_cast<int64_t>(T - 1) * ld_adv + col;
     body.v1 = body.valid ? __ldg(value + static_cast<int64_t>(T) * ld_value + col) : 0.f;
     Pipe::template run<true>(maps, dtab, T, col0, body);
@@ -228,6 +236,8 @@ __global__ void __launch_bounds__(128) gae_fwd_generic(const float* __restrict__
     body.valid = col < B;
     body.m1 = 0.0;
     body.m2 = 0.0;
+    body.p1 = 0.f;
+    body.p2 = 0.f;
     if (!MOM && !body.valid) return;
     if (body.valid) {
         body.g = 0.f;

@@ -77,7 +77,8 @@ int hpc_rll_gae_backward_ld(const float* grad_adv, int64_t ld_grad_adv, float* g
                             float* grad_reward, int64_t ld_grad_reward, int64_t T, int64_t B, double gamma,
                             double lambda, void* stream);
 /* GAE forward that also returns the raw moments of the advantages it writes:
- *   moments[0] = sum(adv), moments[1] = sum(adv^2)   (fp64, device memory, fixed summation order)
+ *   moments[0] = sum(adv), moments[1] = sum(adv^2)   (fp64, device memory, fixed summation order; each
+ *   column folds fp32 runs of 16 rows into fp64 accumulators)
  * for the normalisation (adv - adv.mean()) / (adv.std() + 1e-8) that precedes ppo_error
  * (/root/reference/hpc_rll/origin/ppo.py:43-47) -- fused here so that `adv` is not re-read twice for
  * mean and std.  Data-parallel callers all-reduce(SUM) `moments` before hpc_rll_adv_stats.

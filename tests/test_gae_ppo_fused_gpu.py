@@ -59,11 +59,13 @@ def test_chain_vs_oracle(T, B, N, use_w, dual):
                          inp["value_new"], inp["value_old"], inp["return_"], inp["weight"], hp["gamma"], hp["lambda_"],
                          hp["clip_ratio"], hp["use_value_clip"], hp["dual_clip"], coef)
     assert np.array_equal(r["adv"], o["adv"]), "GAE forward must stay bit-exact with moments on"
-    # both sides take the moments in fp64 and round once: the two statistics agree to an fp32 ulp
+    # moments are accumulated in fp64 (GPU: over fp32 runs of 16 rows): the statistics agree to ~an fp32 ulp
     assert abs(r["stats"][0] - o["adv_mean"]) <= 1e-6 * max(1.0, abs(o["adv_mean"]))
     assert abs(r["stats"][1] - o["adv_denom"]) <= 1e-6 * o["adv_denom"]
-    for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss", "approx_kl", "clipfrac")):
+    for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss", "approx_kl")):
         close(r["losses"][k], o[nm], nm)
+    # clipfrac counts threshold crossings: a ratio within an ulp of 1 +- clip may fall either side
+    assert abs(r["losses"][4] - o["clipfrac"]) <= max(1e-5, 2.0 / (T * B))
     close(r["grad_logits_new"], o["grad_logits_new"], "grad_logits_new")
     close(r["grad_value_new"], o["grad_value_new"], "grad_value_new")
 
@@ -133,8 +135,9 @@ def test_moments_sharded_equals_whole():
         m, _ = moments(value[:, b0:b1], reward[:, b0:b1])
         parts += m
     a64 = adv.astype(np.float64)
-    assert abs(whole[0] - a64.sum()) <= 1e-9 * max(1.0, np.abs(a64).sum())
-    assert abs(whole[1] - np.square(a64).sum()) <= 1e-12 * np.square(a64).sum()
+    # runs of 16 rows are summed in fp32 before they are folded into the fp64 accumulators
+    assert abs(whole[0] - a64.sum()) <= 2e-7 * np.abs(a64).sum()
+    assert abs(whole[1] - np.square(a64).sum()) <= 2e-7 * np.square(a64).sum()
     assert np.allclose(parts, whole, rtol=1e-12, atol=1e-9)
 
 

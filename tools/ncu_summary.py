@@ -27,23 +27,35 @@ KEYS = [
 
 
 def main():
-    rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else ""
+    """one report:   ncu_summary.py a.ncu-rep out.md "title"
+    several reports: ncu_summary.py --many out.md "title" a.ncu-rep b.ncu-rep ...   (one section per kernel)"""
+    if sys.argv[1] == "--many":
+        out, title, reps = sys.argv[2], sys.argv[3], sys.argv[4:]
+    else:
+        reps, out, title = [sys.argv[1]], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else ""
+    with open(out, "w") as f:
+        f.write("# %s\n\nsource: %s (ncu --set full --clock-control none), read with `ncu -i ... --page raw --csv`\n\n"
+                % (title, ", ".join("`%s`" % r for r in reps)))
+        for rep in reps:
+            summarise(rep, f)
+
+
+def summarise(rep, f):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    with open(out, "w") as f:
-        f.write("# %s\n\nsource: `%s` (ncu --set full --clock-control none), read with `ncu -i ... --page raw --csv`\n\n"
-                % (title, rep))
+    if True:
         for r in rows[2:]:
             f.write("## %s\n\n| metric | value | unit |\n|---|---|---|\n" % r[idx["Kernel Name"]])
             for k in KEYS:
                 if k in idx:
                     f.write("| %s | %s | %s |\n" % (k, r[idx[k]], units[idx[k]]))
-            try:
-                rd = float(r[idx["dram__bytes_read.sum"]])
-                wr = float(r[idx["dram__bytes_write.sum"]])
-                f.write("| dram traffic (read+write) | %.3f | %s |\n" % (rd + wr, units[idx["dram__bytes_read.sum"]]))
+            try:  # the two columns can carry different units (e.g. Gbyte vs Mbyte)
+                scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6}
+                rd = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]]
+                wr = float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+                f.write("| dram traffic (read+write) | %.3f | Mbyte |\n" % (rd + wr))
             except Exception:
                 pass
             f.write("\n")
