@@ -46,7 +46,7 @@ def run_q(inp, gamma, rescale, coef):
 
 @pytest.mark.parametrize("rescale", [False, True])
 @pytest.mark.parametrize("T,B,N,use_w", [(1024, 64, 64, False), (5, 4096, 6, True), (1, 7, 3, True), (30, 4, 1, True),
-                                          (3, 70001, 18, True), (5, 1000, 7, False)])
+                                          (3, 70001, 18, True), (5, 1000, 7, False), (2, 9, 2048, False)])
 def test_q_nstep_vs_oracle(T, B, N, use_w, rescale):
     need_cuda()
     g = rng(T + B + N + int(rescale))
@@ -147,7 +147,8 @@ def run_qrdqn(inp, gamma, coef):
 @pytest.mark.parametrize("tau,T,B,N,use_w,use_vg", [(39, 10, 89, 67, False, True), (64, 5, 2000, 8, True, False),
                                                      (8, 5, 6, 4, False, False), (1, 1, 4, 1, True, False),
                                                      (32, 3, 100, 3, True, True), (33, 3, 50, 2, False, False),
-                                                     (130, 2, 40, 2, True, False), (200, 1, 9, 1, False, True)])
+                                                     (130, 2, 40, 2, True, False), (200, 1, 9, 1, False, True),
+                                                     (64, 2, 33, 20, False, False)])
 def test_qrdqn_vs_oracle(tau, T, B, N, use_w, use_vg):
     need_cuda()
     g = rng(tau * 3 + T + B + N)
