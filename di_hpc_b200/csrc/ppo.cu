@@ -212,8 +212,8 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd_loop(const float* __restrict
         mo = warp_max(mo);
         float sn = 0.f, so = 0.f;
         for (int k = lane; k < N; k += 32) {
-            sn += expf(xn[k] - mn);
-            so += expf(xo[k] - mo);
+            sn += exp_term(xn[k] - mn);
+            so += exp_term(xo[k] - mo);
         }
         sn = warp_sum(sn);
         so = warp_sum(so);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(256) ppo_rows_fwd_loop(const float* __restrict
         float h = 0.f;
         for (int k = lane; k < N; k += 32) {
             const float lp = row_logp<true>(xn[k], mn, lsn);
-            h += expf(lp) * lp;
+            h += exp_term(lp) * lp;
         }
         const float H = -warp_sum(h);
         if (lane == 0) {

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kStageRows) softmax_grad_rows_staged_kernel(
             const float e2 = ENT ? s2 * (w ? w[row] : 1.f) : 0.f;
             for (int k = 0; k < N; ++k) {
                 const float xv = x[k];
-                const float p = expf(fmaxf(xv - m, kNegBig)) * inv_s;
+                const float p = exp_term(fmaxf(xv - m, kNegBig)) * inv_s;
                 float gq = c * ((k == a ? 1.f : 0.f) - p);
                 if (ENT) gq += e2 * (-p * (fmaxf(row_logp<CAT>(xv, m, logs), kNegBig) + H));
                 x[k] = gq;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_loop_kernel(const float
         for (int k = lane; k < N; k += 32) m = fmaxf(m, x[k]);
         m = warp_max(m);
         float s = 0.f;
-        for (int k = lane; k < N; k += 32) s += expf(x[k] - m);
+        for (int k = lane; k < N; k += 32) s += exp_term(x[k] - m);
         s = warp_sum(s);
         const float logs = logf(s);
         float H = 0.f;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_loop_kernel(const float
             float h = 0.f;
             for (int k = lane; k < N; k += 32) {
                 const float l = row_logp<CAT>(x[k], m, logs);
-                h += expf(l) * l;
+                h += exp_term(l) * l;
             }
             H = -warp_sum(h);
         }
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_loop_kernel(const float
         const float e2 = ENT ? s2 * (w ? w[row] : 1.f) : 0.f;
         for (int k = lane; k < N; k += 32) {
             const float l = row_logp<CAT>(x[k], m, logs);
-            const float p = expf(l);
+            const float p = exp_term(l);
             float gq = c * ((k == a ? 1.f : 0.f) - p);
             if (ENT) gq += e2 * (-p * (l + H));
             grad[row * N + k] = gq;

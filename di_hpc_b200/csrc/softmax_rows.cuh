@@ -44,6 +44,17 @@ inline RowGeom row_geom(int64_t N, bool aligned) {
 // same guard torch.distributions.Categorical.entropy applies (clamp to finfo.min) for -inf logits
 constexpr float kNegBig = -3.0e38f;
 
+// e^d for the N-wide softmax terms (d = x - max <= 0, or a log-probability): FMUL + MUFU.EX2 instead of
+// expf's 9 instructions -- the row kernels are issue-bound at small N (profiles/r01_ncu_ops.md).
+// Error budget: ex2.approx is good to 2 ulp; rounding d*log2(e) adds a relative |d| * 6e-8, so a term e^d
+// is off by at most |d| e^d * 6e-8 <= 2.2e-8 of the row's largest term -- far inside the 1e-5 parity bar
+// (SURVEY.md 8c).  Per-row scalars (importance ratios) keep expf.  exp_term(-3e38) = 0 like expf.
+__device__ __forceinline__ float exp_term(float d) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d * 1.4426950408889634f));
+    return r;
+}
+
 __device__ __forceinline__ float group_max(float v, int G) {
     for (int o = G >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
@@ -95,7 +106,7 @@ struct RowRegs {
 #pragma unroll
         for (int i = 0; i < NE; ++i) {
             const float d = fmaxf(x[i] - m, kNegBig);
-            const float ei = expf(d);  // masked slots: exp(-3e38) = 0
+            const float ei = exp_term(d);  // masked slots: exp(-3e38) = 0
             ss += ei;
             if (WANT_T) tt = fmaf(ei, d, tt);
             if (KEEP_E) e[i] = ei;
@@ -214,7 +225,7 @@ __device__ __forceinline__ void staged_stats(const float* __restrict__ x, int N,
     float ss = 0.f, tt = 0.f;
     for (int k = 0; k < N; ++k) {
         const float d = fmaxf(x[k] - mm, kNegBig);
-        const float e = expf(d);
+        const float e = exp_term(d);
         ss += e;
         if (WANT_T) tt = fmaf(e, d, tt);
     }

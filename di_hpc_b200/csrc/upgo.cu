@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) upgo_rows_fwd_loop(const float* __restric
         for (int k = lane; k < N; k += 32) m = fmaxf(m, x[k]);
         m = warp_max(m);
         float s = 0.f;
-        for (int k = lane; k < N; k += 32) s += expf(x[k] - m);
+        for (int k = lane; k < N; k += 32) s += exp_term(x[k] - m);
         s = warp_sum(s);
         if (lane == 0) metric[row] = row_logp<false>(x[action[row]], m, logf(s));
     }

@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd_loop(const float* __restr
         mb = warp_max(mb);
         float st = 0.f, sb = 0.f;
         for (int k = lane; k < N; k += 32) {
-            st += expf(xt[k] - mt);
-            sb += expf(xb[k] - mb);
+            st += exp_term(xt[k] - mt);
+            sb += exp_term(xb[k] - mb);
         }
         st = warp_sum(st);
         sb = warp_sum(sb);
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd_loop(const float* __restr
         float h = 0.f;
         for (int k = lane; k < N; k += 32) {
             const float lp = row_logp<true>(xt[k], mt, lst);
-            h += expf(lp) * lp;
+            h += exp_term(lp) * lp;
         }
         const float H = -warp_sum(h);
         if (lane == 0) {
