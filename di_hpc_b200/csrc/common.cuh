@@ -44,6 +44,7 @@ void clear_error();
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }
 
 // number of SMs of the current device (cached)
 int sm_count();
@@ -143,6 +144,7 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 
 // streaming (evict-first) global accesses for data touched exactly once
 __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream2(float2* p, float2 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream4(float4* p, float4 v) { __stcs(p, v); }
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ float4 ld_stream4(const float4* p) { return __ldcs(p); }

@@ -75,7 +75,7 @@ __device__ __forceinline__ void ppo_sample(const PpoParams& P, float lpn, float 
     val_coef = 0.5f * dval * w * P.inv_n;
 }
 
-template <int KMAX, bool VEC>
+template <int KMAX, int WIDTH>
 __global__ void __launch_bounds__(256, KMAX >= 8 ? 1 : 3) ppo_rows_fwd(const float* __restrict__ logits_new,
                                                      const float* __restrict__ logits_old,
                                                      const int64_t* __restrict__ action,
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256, KMAX >= 8 ? 1 : 3) ppo_rows_fwd(const flo
                                                      const float* __restrict__ weight, float* __restrict__ pol_coef,
                                                      float* __restrict__ val_coef, double* __restrict__ partials,
                                                      const PpoParams P, int64_t R, int N, int G, int log2G) {
-    using Row = RowRegs<KMAX, VEC>;
+    using Row = RowRegs<KMAX, WIDTH>;
     __shared__ double red[5 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (G - 1), gw = lane >> log2G;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256, KMAX >= 8 ? 1 : 3) ppo_rows_fwd(const flo
     const int rows_per_block = rows_per_warp * 8;
     double acc[5] = {0, 0, 0, 0, 0};
     const AdvNorm norm(P);
-    constexpr bool PF = KMAX <= 2;  // software pipeline (see softmax_rows.cu)
+    constexpr bool PF = Row::NE <= 8;  // software pipeline (see softmax_rows.cu)
     Row rn, ro, nn, no;
     int a, na = -1;
     {
@@ -267,10 +267,10 @@ static int ppo_forward_impl(const float* logits_new, const float* logits_old, co
     P.inv_n = static_cast<float>(inv_n);
     P.adv_stats = adv_stats;
     double* partials = static_cast<double*>(workspace);
-    const RowGeom ge = row_geom(N, aligned16(logits_new) && aligned16(logits_old));
+    const RowGeom ge = row_geom(N, logits_new, logits_old);
     int log2G = 0;
     while ((1 << log2G) < ge.G) ++log2G;
-    const bool staged = use_staged_rows(N, ge.vec != 0);
+    const bool staged = use_staged_rows(N, ge.width);
     const unsigned grid = rows_grid(B, staged ? kStageRows : (ge.kmax == 0 ? 8 : (32 / ge.G) * 8));
     const int n = static_cast<int>(N);
 #define HPC_PPO_ROWS(K, V)                                                                                       \

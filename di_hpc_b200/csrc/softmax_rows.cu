@@ -8,7 +8,7 @@
 
 namespace hpcrll {
 
-template <int KMAX, bool VEC, bool ENT, bool CAT>
+template <int KMAX, int WIDTH, bool ENT, bool CAT>
 __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __restrict__ logits,
                                                                  const int64_t* __restrict__ action,
                                                                  const float* __restrict__ c1,
@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
                                                                  const float* __restrict__ g2, float inv_n,
                                                                  float* __restrict__ grad, int64_t R, int N, int G,
                                                                  int log2G) {
-    using Row = RowRegs<KMAX, VEC>;
+    using Row = RowRegs<KMAX, WIDTH>;
     constexpr int W = Row::W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (G - 1), gw = lane >> log2G;
@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
     const float s1 = __ldg(g1);
     const float s2 = ENT ? __ldg(g2) * inv_n : 0.f;
     // software pipeline (small rows only): the next row block's loads fly while this one is reduced
-    constexpr bool PF = KMAX <= 2;
+    constexpr bool PF = Row::NE <= 8;
     Row rr, nx;
     {
         const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
@@ -59,9 +59,11 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
             }
             const int e0 = rr.index(j, 0, G, lig);
             if (active && e0 < N) {
-                if (VEC)
+                if (W == 4)
                     st_stream4(reinterpret_cast<float4*>(grad + row * N + e0),
                                make_float4(o[0], o[W > 1 ? 1 : 0], o[W > 2 ? 2 : 0], o[W > 3 ? 3 : 0]));
+                else if (W == 2)
+                    st_stream2(reinterpret_cast<float2*>(grad + row * N + e0), make_float2(o[0], o[W > 1 ? 1 : 0]));
                 else
                     st_stream(grad + row * N + e0, o[0]);
             }
@@ -155,8 +157,8 @@ template <bool ENT, bool CAT>
 static int launch_grad_t(const float* logits, const int64_t* action, const float* c1, const float* w,
                          const float* g1, const float* g2, float inv_n, float* grad, int64_t R, int N,
                          cudaStream_t stream) {
-    const RowGeom ge = row_geom(N, aligned16(logits) && aligned16(grad));
-    if (use_staged_rows(N, ge.vec != 0)) {
+    const RowGeom ge = row_geom(N, logits, grad);
+    if (use_staged_rows(N, ge.width)) {
         const int P = stage_pitch(N);
         const unsigned sgrid = rows_grid(R, kStageRows);
         const int al = aligned16(logits) && aligned16(grad) ? 1 : 0;

@@ -23,14 +23,25 @@ namespace hpcrll {
 struct RowGeom {
     int G;      // lanes per row (power of two <= 32)
     int kmax;   // register chunks per lane: 1, 2, 4 or 8 (0 = N too large for registers: looping kernel)
-    int vec;    // 1: float4 chunks (N % 4 == 0 and 16B-aligned base), 0: scalar chunks
+    int width;  // floats per chunk: 4 (N % 4 == 0, 16B-aligned bases), 2 (N even, 8B-aligned: Atari's 6 / 18), 1
 };
 
-inline RowGeom row_geom(int64_t N, bool aligned) {
+// p0 / p1: the tensors the kernel reads or writes row-wise (p1 may be null)
+inline RowGeom row_geom(int64_t N, const void* p0, const void* p1 = nullptr) {
     RowGeom g;
-    g.vec = (aligned && (N % 4) == 0) ? 1 : 0;
-    const int64_t chunks = g.vec ? N / 4 : N;  // chunk = one load per lane
+    const bool a16 = aligned16(p0) && (!p1 || aligned16(p1)), a8 = aligned8(p0) && (!p1 || aligned8(p1));
+    g.width = (a16 && N % 4 == 0) ? 4 : ((a8 && N % 2 == 0) ? 2 : 1);
+    const int64_t chunks = N / g.width;  // chunk = one load per lane
     int G = 1;
+    if (g.width == 2) {
+        // 64-bit chunks: up to 8 per lane (same registers as 4 float4) and an EXACT chunk count, so N=6 is one
+        // lane x 3 chunks and N=18 two lanes x 5 chunks (one shuffle round, 10 % idle slots)
+        while (G < 32 && chunks > static_cast<int64_t>(G) * 8) G <<= 1;
+        g.G = G;
+        const int64_t per_lane = (chunks + G - 1) / G;
+        g.kmax = per_lane <= 8 ? static_cast<int>(per_lane) : 0;
+        return g;
+    }
     while (G < 32 && chunks > static_cast<int64_t>(G) * 4) G <<= 1;  // aim at <= 4 chunks per lane
     g.G = G;
     const int64_t per_lane = (chunks + G - 1) / G;
@@ -65,9 +76,10 @@ __device__ __forceinline__ float group_sum(float v, int G) {
 }
 
 // One row held across a group of G lanes.  Element index of x[j*W+q] is ((j*G + lig)*W + q).
-template <int KMAX, bool VEC>
+template <int KMAX, int WIDTH>
 struct RowRegs {
-    static constexpr int W = VEC ? 4 : 1;
+    static_assert(WIDTH == 1 || WIDTH == 2 || WIDTH == 4, "chunk width");
+    static constexpr int W = WIDTH;
     static constexpr int NE = KMAX * W;
     float x[NE];
 
@@ -79,13 +91,18 @@ struct RowRegs {
 #pragma unroll
         for (int j = 0; j < KMAX; ++j) {
             const int e0 = (j * G + lig) * W;
-            if (VEC) {
+            if (W == 4) {
                 float4 v = make_float4(kNegBig, kNegBig, kNegBig, kNegBig);
                 if (active && e0 < N) v = __ldg(reinterpret_cast<const float4*>(row + e0));
                 x[j * W + 0] = v.x;
                 x[j * W + (W > 1 ? 1 : 0)] = v.y;
                 x[j * W + (W > 2 ? 2 : 0)] = v.z;
                 x[j * W + (W > 3 ? 3 : 0)] = v.w;
+            } else if (W == 2) {
+                float2 v = make_float2(kNegBig, kNegBig);
+                if (active && e0 < N) v = __ldg(reinterpret_cast<const float2*>(row + e0));
+                x[j * W + 0] = v.x;
+                x[j * W + (W > 1 ? 1 : 0)] = v.y;
             } else {
                 x[j] = (active && e0 < N) ? __ldg(row + e0) : kNegBig;
             }
@@ -145,8 +162,9 @@ __device__ __forceinline__ float row_logp(float x, float m, float logs) {
 constexpr int kStageRows = 256;
 inline int stage_pitch(int N) { return N | 1; }
 // measured (profiles/r01_ops.md): for N <= 8 the per-lane scalar chunks are as fast or faster; from N = 9 the
-// staged path wins (N=18: 3.3 -> 2.0 ms for V-trace at T=512, B=32768)
-inline bool use_staged_rows(int64_t N, bool vec_eligible) { return N > 8 && N <= 32 && !vec_eligible; }
+// staged path wins (N=18: 3.3 -> 2.0 ms for V-trace at T=512, B=32768).  Rows that can be read in 64-bit or
+// 128-bit chunks (`width` > 1) stay on the register path.
+inline bool use_staged_rows(int64_t N, int width) { return N > 8 && N <= 32 && width == 1; }
 inline size_t stage_bytes(int N, int tiles) { return static_cast<size_t>(tiles) * kStageRows * stage_pitch(N) * sizeof(float); }
 
 // copy rows [row0, row0 + kStageRows) of a contiguous (R, N) tensor into tile[r * P + c]
@@ -260,20 +278,29 @@ struct FinSpec {
 };
 int launch_finalize_terms(const double* partials, const FinSpec& spec, int nterms, float* out, cudaStream_t stream);
 
-// dispatch helper: expands to the KMAX/VEC instantiation selected by a RowGeom
-#define HPC_ROW_DISPATCH(ge, LAUNCH)                       \
-    do {                                                   \
-        if ((ge).vec) {                                    \
-            if ((ge).kmax == 1) { LAUNCH(1, true); }       \
-            else if ((ge).kmax == 2) { LAUNCH(2, true); }  \
-            else if ((ge).kmax == 4) { LAUNCH(4, true); }  \
-            else { LAUNCH(8, true); }                      \
-        } else {                                           \
-            if ((ge).kmax == 1) { LAUNCH(1, false); }      \
-            else if ((ge).kmax == 2) { LAUNCH(2, false); } \
-            else if ((ge).kmax == 4) { LAUNCH(4, false); } \
-            else { LAUNCH(8, false); }                     \
-        }                                                  \
+// dispatch helper: expands to the KMAX/WIDTH instantiation selected by a RowGeom
+#define HPC_ROW_DISPATCH_W(ge, LAUNCH, WD)              \
+    do {                                                \
+        if ((ge).kmax == 1) { LAUNCH(1, WD); }          \
+        else if ((ge).kmax == 2) { LAUNCH(2, WD); }     \
+        else if ((ge).kmax == 4) { LAUNCH(4, WD); }     \
+        else { LAUNCH(8, WD); }                         \
+    } while (0)
+#define HPC_ROW_DISPATCH(ge, LAUNCH)                                   \
+    do {                                                               \
+        if ((ge).width == 4) HPC_ROW_DISPATCH_W(ge, LAUNCH, 4);        \
+        else if ((ge).width == 2) {                                    \
+            switch ((ge).kmax) {                                       \
+                case 1: LAUNCH(1, 2); break;                           \
+                case 2: LAUNCH(2, 2); break;                           \
+                case 3: LAUNCH(3, 2); break;                           \
+                case 4: LAUNCH(4, 2); break;                           \
+                case 5: LAUNCH(5, 2); break;                           \
+                case 6: LAUNCH(6, 2); break;                           \
+                case 7: LAUNCH(7, 2); break;                           \
+                default: LAUNCH(8, 2); break;                          \
+            }                                                          \
+        } else HPC_ROW_DISPATCH_W(ge, LAUNCH, 1);                      \
     } while (0)
 
 }  // namespace hpcrll

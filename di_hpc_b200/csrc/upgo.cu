@@ -17,17 +17,17 @@
 
 namespace hpcrll {
 
-template <int KMAX, bool VEC>
+template <int KMAX, int WIDTH>
 __global__ void __launch_bounds__(256) upgo_rows_fwd(const float* __restrict__ logits,
                                                       const int64_t* __restrict__ action,
                                                       float* __restrict__ metric, int64_t R, int N, int G,
                                                       int log2G) {
-    using Row = RowRegs<KMAX, VEC>;
+    using Row = RowRegs<KMAX, WIDTH>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (G - 1), gw = lane >> log2G;
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
-    constexpr bool PF = KMAX <= 2;  // software pipeline (see softmax_rows.cu)
+    constexpr bool PF = Row::NE <= 8;  // software pipeline (see softmax_rows.cu)
     Row rr, nx;
     int a, na = -1;
     {
@@ -228,10 +228,10 @@ int hpc_rll_upgo_forward(const float* target_output, const float* rhos, const in
     double* partials = reinterpret_cast<double*>(ws + align_up_(R * 4, 256));
     const double inv_n = 1.0 / (static_cast<double>(T) * static_cast<double>(global_B));
 
-    const RowGeom ge = row_geom(N, aligned16(target_output));
+    const RowGeom ge = row_geom(N, target_output);
     int log2G = 0;
     while ((1 << log2G) < ge.G) ++log2G;
-    const bool staged = use_staged_rows(N, ge.vec != 0);
+    const bool staged = use_staged_rows(N, ge.width);
     const unsigned grid1 = rows_grid(R, staged ? kStageRows : (ge.kmax == 0 ? 8 : (32 / ge.G) * 8));
     const int n = static_cast<int>(N);
 #define HPC_UP_ROWS(K, V) upgo_rows_fwd<K, V><<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n, ge.G, log2G)

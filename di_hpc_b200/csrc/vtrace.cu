@@ -25,14 +25,14 @@ namespace hpcrll {
 // ------------------------------------------------------------------------------------------------
 // forward stage 1: rows
 // ------------------------------------------------------------------------------------------------
-template <int KMAX, bool VEC>
+template <int KMAX, int WIDTH>
 __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__ target,
                                                         const float* __restrict__ behaviour,
                                                         const int64_t* __restrict__ action,
                                                         const float* __restrict__ weight, float* __restrict__ is_out,
                                                         float* __restrict__ logp_out, double* __restrict__ partials,
                                                         int64_t R, int N, int G, int log2G) {
-    using Row = RowRegs<KMAX, VEC>;
+    using Row = RowRegs<KMAX, WIDTH>;
     __shared__ double red[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int lig = lane & (G - 1), gw = lane >> log2G;
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__
     const int rows_per_block = rows_per_warp * 8;
     double ent_acc = 0.0;
     // software pipeline: next row block's loads are issued before this block is reduced
-    constexpr bool PF = KMAX <= 2;
+    constexpr bool PF = Row::NE <= 8;
     Row rt, rbh, nt, nb;
     int a, na = -1;
     {
@@ -352,11 +352,11 @@ int hpc_rll_vtrace_forward(const float* target_output, const float* behaviour_ou
     const double inv_n = 1.0 / (static_cast<double>(T) * static_cast<double>(global_B));
 
     // ---- stage 1: rows ----
-    const RowGeom ge = row_geom(N, aligned16(target_output) && aligned16(behaviour_output));
+    const RowGeom ge = row_geom(N, target_output, behaviour_output);
     int log2G = 0;
     while ((1 << log2G) < ge.G) ++log2G;
     const int rows_per_block = (32 / ge.G) * 8;
-    const bool staged = use_staged_rows(N, ge.vec != 0);
+    const bool staged = use_staged_rows(N, ge.width);
     const unsigned grid1 = rows_grid(R, staged ? kStageRows : (ge.kmax == 0 ? 8 : rows_per_block));
     const int n = static_cast<int>(N);
 #define HPC_VT_ROWS(K, V)                                                                                       \
