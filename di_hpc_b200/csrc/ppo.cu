@@ -76,7 +76,7 @@ __device__ __forceinline__ void ppo_sample(const PpoParams& P, float lpn, float 
 }
 
 template <int KMAX, int WIDTH>
-__global__ void __launch_bounds__(256, KMAX >= 8 ? 1 : 3) ppo_rows_fwd(const float* __restrict__ logits_new,
+__global__ void __launch_bounds__(256, KMAX * WIDTH >= 32 ? 1 : (KMAX * WIDTH >= 24 ? 2 : 3)) ppo_rows_fwd(const float* __restrict__ logits_new,
                                                      const float* __restrict__ logits_old,
                                                      const int64_t* __restrict__ action,
                                                      const float* __restrict__ value_new,

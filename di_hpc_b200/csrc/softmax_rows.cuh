@@ -22,7 +22,7 @@ namespace hpcrll {
 // geometry of the row -> lane mapping, decided on the host
 struct RowGeom {
     int G;      // lanes per row (power of two <= 32)
-    int kmax;   // register chunks per lane: 1, 2, 4 or 8 (0 = N too large for registers: looping kernel)
+    int kmax;   // register chunks per lane, exact: 1..8 (0 = N too large for registers: looping kernel)
     int width;  // floats per chunk: 4 (N % 4 == 0, 16B-aligned bases), 2 (N even, 8B-aligned: Atari's 6 / 18), 1
 };
 
@@ -32,20 +32,15 @@ inline RowGeom row_geom(int64_t N, const void* p0, const void* p1 = nullptr) {
     const bool a16 = aligned16(p0) && (!p1 || aligned16(p1)), a8 = aligned8(p0) && (!p1 || aligned8(p1));
     g.width = (a16 && N % 4 == 0) ? 4 : ((a8 && N % 2 == 0) ? 2 : 1);
     const int64_t chunks = N / g.width;  // chunk = one load per lane
+    // lanes per row: the smallest power of two that leaves <= 4 float4 (or <= 8 narrower) chunks per lane; the
+    // chunk count per lane is EXACT (kernels are instantiated for 1..8), so N=6 is one lane x 3 float2, N=18 two
+    // lanes x 5 float2, N=24 two lanes x 3 float4 -- the row kernels are issue-bound, idle register slots cost
+    const int64_t cap = g.width == 4 ? 4 : 8;
     int G = 1;
-    if (g.width == 2) {
-        // 64-bit chunks: up to 8 per lane (same registers as 4 float4) and an EXACT chunk count, so N=6 is one
-        // lane x 3 chunks and N=18 two lanes x 5 chunks (one shuffle round, 10 % idle slots)
-        while (G < 32 && chunks > static_cast<int64_t>(G) * 8) G <<= 1;
-        g.G = G;
-        const int64_t per_lane = (chunks + G - 1) / G;
-        g.kmax = per_lane <= 8 ? static_cast<int>(per_lane) : 0;
-        return g;
-    }
-    while (G < 32 && chunks > static_cast<int64_t>(G) * 4) G <<= 1;  // aim at <= 4 chunks per lane
+    while (G < 32 && chunks > static_cast<int64_t>(G) * cap) G <<= 1;
     g.G = G;
     const int64_t per_lane = (chunks + G - 1) / G;
-    g.kmax = per_lane <= 1 ? 1 : (per_lane <= 2 ? 2 : (per_lane <= 4 ? 4 : (per_lane <= 8 ? 8 : 0)));
+    g.kmax = per_lane <= 8 ? static_cast<int>(per_lane) : 0;
     return g;
 }
 
@@ -279,28 +274,22 @@ struct FinSpec {
 int launch_finalize_terms(const double* partials, const FinSpec& spec, int nterms, float* out, cudaStream_t stream);
 
 // dispatch helper: expands to the KMAX/WIDTH instantiation selected by a RowGeom
-#define HPC_ROW_DISPATCH_W(ge, LAUNCH, WD)              \
-    do {                                                \
-        if ((ge).kmax == 1) { LAUNCH(1, WD); }          \
-        else if ((ge).kmax == 2) { LAUNCH(2, WD); }     \
-        else if ((ge).kmax == 4) { LAUNCH(4, WD); }     \
-        else { LAUNCH(8, WD); }                         \
-    } while (0)
-#define HPC_ROW_DISPATCH(ge, LAUNCH)                                   \
-    do {                                                               \
-        if ((ge).width == 4) HPC_ROW_DISPATCH_W(ge, LAUNCH, 4);        \
-        else if ((ge).width == 2) {                                    \
-            switch ((ge).kmax) {                                       \
-                case 1: LAUNCH(1, 2); break;                           \
-                case 2: LAUNCH(2, 2); break;                           \
-                case 3: LAUNCH(3, 2); break;                           \
-                case 4: LAUNCH(4, 2); break;                           \
-                case 5: LAUNCH(5, 2); break;                           \
-                case 6: LAUNCH(6, 2); break;                           \
-                case 7: LAUNCH(7, 2); break;                           \
-                default: LAUNCH(8, 2); break;                          \
-            }                                                          \
-        } else HPC_ROW_DISPATCH_W(ge, LAUNCH, 1);                      \
+#define HPC_ROW_DISPATCH_W(ge, LAUNCH, WD)      \
+    switch ((ge).kmax) {                        \
+        case 1: LAUNCH(1, WD); break;           \
+        case 2: LAUNCH(2, WD); break;           \
+        case 3: LAUNCH(3, WD); break;           \
+        case 4: LAUNCH(4, WD); break;           \
+        case 5: LAUNCH(5, WD); break;           \
+        case 6: LAUNCH(6, WD); break;           \
+        case 7: LAUNCH(7, WD); break;           \
+        default: LAUNCH(8, WD); break;          \
+    }
+#define HPC_ROW_DISPATCH(ge, LAUNCH)                                 \
+    do {                                                             \
+        if ((ge).width == 4) { HPC_ROW_DISPATCH_W(ge, LAUNCH, 4) }   \
+        else if ((ge).width == 2) { HPC_ROW_DISPATCH_W(ge, LAUNCH, 2) } \
+        else { HPC_ROW_DISPATCH_W(ge, LAUNCH, 1) }                   \
     } while (0)
 
 }  // namespace hpcrll

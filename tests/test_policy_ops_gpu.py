@@ -231,3 +231,44 @@ def test_masked_actions_with_minus_inf_logits():
     assert np.all(gt[:, :, k] == 0)
     close(np.delete(gt, k, axis=2), o["grad_target_output"], "grad_target_output")
     close(gv, o["grad_value"], "grad_value")
+
+
+# ----------------------------------------------------------------------------------------- row geometry sweep
+SWEEP_N = list(range(1, 41)) + [44, 48, 52, 60, 66, 100, 132, 250, 255, 257]
+
+
+@pytest.mark.parametrize("N", SWEEP_N)
+def test_row_geometry_sweep(N):
+    """Every (chunk width, lanes per row, chunks per lane) combination `row_geom` can pick -- 128-bit / 64-bit /
+    scalar chunks with 1..8 chunks per lane, staged rows for odd 9 <= N <= 31, the looping kernel beyond -- on all
+    three ops that share the row machinery, ragged row counts included."""
+    need_cuda()
+    g = rng(1000 + N)
+    T, B = 3, 45
+    inp = vtrace_inputs(g, T, B, N, True)
+    coef = [1.0, 0.5, -0.25]
+    losses, gt, gv = run_vtrace(inp, HP2, coef)
+    o = orc.vtrace(inp["target_output"], inp["behaviour_output"], inp["action"], inp["value"], inp["reward"],
+                   inp["weight"], coef=coef, **HP2)
+    for i, name in enumerate(("policy_loss", "value_loss", "entropy_loss")):
+        close(losses[i], o[name], "vtrace " + name)
+    close(gt, o["grad_target_output"], "vtrace grad_target_output")
+    close(gv, o["grad_value"], "vtrace grad_value")
+
+    up = dict(target_output=inp["target_output"], rhos=(g.random((T, B)) * 2).astype(np.float32), action=inp["action"],
+              rewards=inp["reward"], bootstrap_values=inp["value"])
+    loss, gt = run_upgo(up, -0.7)
+    o = orc.upgo(up["target_output"], up["rhos"], up["action"], up["rewards"], up["bootstrap_values"], -0.7)
+    close(loss, o["loss"], "upgo loss")
+    close(gt, o["grad_target_output"], "upgo grad_target_output")
+
+    pp = ppo_inputs(g, 131, N, True)
+    c3 = [1.0, 0.5, -0.01]
+    outs, gl, gvn = run_ppo(pp, 0.2, True, None, c3)
+    o = orc.ppo(pp["logits_new"], pp["logits_old"], pp["action"], pp["value_new"], pp["value_old"], pp["adv"],
+                pp["return_"], pp["weight"], 0.2, True, None, c3)
+    for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss", "approx_kl")):
+        close(outs[k], o[nm], "ppo " + nm)
+    assert abs(outs[4] - o["clipfrac"]) <= 2.0 / 131 + 1e-6
+    close(gl, o["grad_logits_new"], "ppo grad_logits_new")
+    close(gvn, o["grad_value_new"], "ppo grad_value_new")
