@@ -75,8 +75,15 @@ __device__ __forceinline__ void ppo_sample(const PpoParams& P, float lpn, float 
     val_coef = 0.5f * dval * w * P.inv_n;
 }
 
+// resident CTAs per SM the register budget is tuned for: two rows (+ their prefetched successors when the row is
+// small) live in registers
+constexpr int ppo_min_blocks(int kmax, int width) {
+    const int ne = kmax * width;
+    return ne >= 32 ? 1 : ((ne >= 20 || (ne == 8 && kmax >= 4)) ? 2 : 3);
+}
+
 template <int KMAX, int WIDTH>
-__global__ void __launch_bounds__(256, KMAX * WIDTH >= 32 ? 1 : (KMAX * WIDTH >= 24 ? 2 : 3)) ppo_rows_fwd(const float* __restrict__ logits_new,
+__global__ void __launch_bounds__(256, ppo_min_blocks(KMAX, WIDTH)) ppo_rows_fwd(const float* __restrict__ logits_new,
                                                      const float* __restrict__ logits_old,
                                                      const int64_t* __restrict__ action,
                                                      const float* __restrict__ value_new,
@@ -95,12 +102,30 @@ __global__ void __launch_bounds__(256, KMAX * WIDTH >= 32 ? 1 : (KMAX * WIDTH >=
     const AdvNorm norm(P);
     constexpr bool PF = Row::NE <= 8;  // software pipeline (see softmax_rows.cu)
     Row rn, ro, nn, no;
-    int a, na = -1;
+    // per-sample scalars travel with the row loads (one iteration ahead), so that their latency is not exposed a
+    // second time after the row statistics (ncu: this kernel was long-scoreboard-bound, 5.8 of 10 stall cycles)
+    struct Scal {
+        float adv, vn, vo, ret, w;
+        int a;
+    };
+    auto load_scal = [&](int64_t r) {
+        Scal sc;
+        const bool ok = r < R;
+        sc.a = ok ? static_cast<int>(__ldg(action + r)) : -1;
+        const bool mine = ok && lig == 0;
+        sc.adv = mine ? __ldg(adv + r) : 0.f;
+        sc.vn = mine ? __ldg(value_new + r) : 0.f;
+        sc.vo = mine ? __ldg(value_old + r) : 0.f;
+        sc.ret = mine ? __ldg(ret + r) : 0.f;
+        sc.w = (mine && weight) ? __ldg(weight + r) : 1.f;
+        return sc;
+    };
+    Scal cur, nxt;
     {
         const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
         rn.load(logits_new + row0 * N, N, G, lig, row0 < R);
         ro.load(logits_old + row0 * N, N, G, lig, row0 < R);
-        a = row0 < R ? static_cast<int>(action[row0]) : -1;
+        cur = load_scal(row0);
     }
     for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
         const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
@@ -109,8 +134,9 @@ __global__ void __launch_bounds__(256, KMAX * WIDTH >= 32 ? 1 : (KMAX * WIDTH >=
         if (PF) {
             nn.load(logits_new + nrow * N, N, G, lig, nrow < R);
             no.load(logits_old + nrow * N, N, G, lig, nrow < R);
-            na = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
+        nxt = load_scal(nrow);
+        const int a = cur.a;
         const float mn = rn.row_max(G), mo = ro.row_max(G);
         float sn, tn, so, to, none[Row::NE];
         rn.template stats<true, false>(G, mn, sn, tn, none);
@@ -121,20 +147,18 @@ __global__ void __launch_bounds__(256, KMAX * WIDTH >= 32 ? 1 : (KMAX * WIDTH >=
         const float selo = row_logp<true>(group_sum(ro.select(a, G, lig), G), mo, lso);
         if (active && lig == 0) {
             float pc, vc;
-            ppo_sample(P, seln, selo, H, norm(adv[row]), value_new[row], value_old[row], ret[row],
-                       weight ? weight[row] : 1.f, acc, pc, vc);
+            ppo_sample(P, seln, selo, H, norm(cur.adv), cur.vn, cur.vo, cur.ret, cur.w, acc, pc, vc);
             pol_coef[row] = pc;
             val_coef[row] = vc;
         }
         if (PF) {
             rn = nn;
             ro = no;
-            a = na;
         } else {
             rn.load(logits_new + nrow * N, N, G, lig, nrow < R);
             ro.load(logits_old + nrow * N, N, G, lig, nrow < R);
-            a = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
+        cur = nxt;
     }
     block_sum<5>(acc, red);
     if (threadIdx.x == 0) {
