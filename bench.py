@@ -253,7 +253,10 @@ def run_ours(args):
     bwd_ms = kernel_ms(bwd, max(K, 20))
     fwd_b, bwd_b = algorithmic_bytes(T, B)
     peak, peak_src = hbm_peak()
-    dom = "gae_bwd_tma" if bwd_ms >= fwd_ms else "gae_fwd_tma"
+    # kernel the library picks at this width (gae.cu pick_cfg): bulk-store output from 256 columns per SM up
+    st = "_st" if B >= 256 * torch.cuda.get_device_properties(dev).multi_processor_count and \
+        "HPC_RLL_CFG_GAE" not in os.environ else ""
+    dom = ("gae_bwd_tma" if bwd_ms >= fwd_ms else "gae_fwd_tma") + st
     dom_ms, dom_b = (bwd_ms, bwd_b) if bwd_ms >= fwd_ms else (fwd_ms, fwd_b)
     achieved = dom_b / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

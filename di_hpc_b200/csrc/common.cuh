@@ -138,6 +138,29 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 2-D tiled TMA store: smem box -> (col0,row0) of the tensor map; elements outside the tensor are clipped.
+// Completion is tracked by bulk async-groups of the issuing thread (commit + wait below).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int col0, int row0, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(col0), "r"(row0), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's bulk groups are still READING shared memory
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// wait until at most N of this thread's bulk groups are pending at all (writes performed)
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// named barrier over `count` threads (a multiple of 32) of the CTA; id 0 is __syncthreads
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

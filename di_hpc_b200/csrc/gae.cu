@@ -222,6 +222,65 @@ __global__ void __launch_bounds__(BT + 32) gae_bwd_tma(const __grid_constant__ T
     if (body.valid) st_stream(body.gv, __fmul_rn(gamma, body.prev));  // row T
 }
 
+// ---- variants with TMA-staged OUTPUT (ScanPipeOut): same arithmetic, results leave as (TT x BT) bulk stores ----
+struct GaeFwdBodyO {
+    float g, v1, gamma, factor;
+    __device__ __forceinline__ void step(int /*t*/, const float (&x)[2], const float (&dt)[2], float (&o)[1]) {
+        const float delta = __fsub_rn(__fadd_rn(x[1], __fmul_rn(gamma, v1)), x[0]);
+        g = __fadd_rn(__fmul_rn(dt[0], delta), __fmul_rn(factor, g));
+        o[0] = div_by_table(g, dt[0], dt[1]);
+        v1 = x[0];
+    }
+};
+
+template <int BT, int TT, int ST>
+__global__ void __launch_bounds__(BT + 32) gae_fwd_tma_st(const __grid_constant__ TmapPack<2> maps,
+                                                           const __grid_constant__ TmapPack<1> omaps,
+                                                           const float* __restrict__ dtab,
+                                                           const float* __restrict__ value, int64_t ld_value, int T,
+                                                           int B, float gamma, float factor) {
+    using Pipe = ScanPipeOut<2, 1, BT, TT, ST, 2>;
+    const int col0 = blockIdx.x * BT;
+    const int col = col0 + threadIdx.x;
+    GaeFwdBodyO body;
+    body.g = 0.f;
+    body.gamma = gamma;
+    body.factor = factor;
+    body.v1 = (threadIdx.x < BT && col < B) ? __ldg(value + static_cast<int64_t>(T) * ld_value + col) : 0.f;
+    Pipe::template run<true>(maps, omaps, dtab, T, col0, body);
+}
+
+struct GaeBwdBodyO {
+    float gh, prev, gamma, factor;
+    __device__ __forceinline__ void step(int /*t*/, const float (&x)[1], const float (&dt)[2], float (&o)[2]) {
+        const float h = __fadd_rn(div_by_table(x[0], dt[0], dt[1]), __fmul_rn(factor, gh));
+        gh = h;
+        const float dd = __fmul_rn(dt[0], h);
+        o[0] = __fsub_rn(__fmul_rn(gamma, prev), dd);  // grad_value[t]
+        o[1] = dd;                                      // grad_reward[t]
+        prev = dd;
+    }
+};
+
+template <int BT, int TT, int ST>
+__global__ void __launch_bounds__(BT + 32) gae_bwd_tma_st(const __grid_constant__ TmapPack<1> maps,
+                                                           const __grid_constant__ TmapPack<2> omaps,
+                                                           const float* __restrict__ dtab,
+                                                           float* __restrict__ grad_value, int64_t ld_gv, int T, int B,
+                                                           float gamma, float factor) {
+    using Pipe = ScanPipeOut<1, 2, BT, TT, ST, 2>;
+    const int col0 = blockIdx.x * BT;
+    const int col = col0 + threadIdx.x;
+    GaeBwdBodyO body;
+    body.gh = 0.f;
+    body.prev = 0.f;
+    body.gamma = gamma;
+    body.factor = factor;
+    Pipe::template run<false>(maps, omaps, dtab, T, col0, body);
+    // row T of grad_value is outside the output tensor map (T rows): one plain store per column
+    if (threadIdx.x < BT && col < B) st_stream(grad_value + static_cast<int64_t>(T) * ld_gv + col, __fmul_rn(gamma, body.prev));
+}
+
 // Generic (no alignment requirements) variants: one thread per column, plain coalesced loads with
 // a 4-deep software prefetch.  Used when a pointer / pitch is not 16-byte aligned so TMA cannot
 // describe the tensor.  Still a CUDA kernel -- there is no CPU path.
@@ -496,12 +555,61 @@ static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab,
     return HPC_RLL_OK;
 }
 
+template <int BT, int TT, int ST>
+static int launch_fwd_tma_st(const float* value, int64_t ldv, const float* reward, int64_t ldr, const float* dtab,
+                             float* adv, int64_t lda, int64_t T, int64_t B, float gamma, float factor,
+                             cudaStream_t stream) {
+    using Pipe = ScanPipeOut<2, 1, BT, TT, ST, 2>;
+    static SmemOptIn opt;
+    auto kernel = gae_fwd_tma_st<BT, TT, ST>;
+    if (int rc0 = opt.ensure(kernel, Pipe::kSmemBytes)) return rc0;
+    TmapPack<2> maps;
+    TmapPack<1> omaps;
+    int rc = make_tmap_2d(&maps.m[0], value, T + 1, B, ldv, TT, BT);
+    if (rc) return rc;
+    rc = make_tmap_2d(&maps.m[1], reward, T, B, ldr, TT, BT);
+    if (rc) return rc;
+    rc = make_tmap_2d(&omaps.m[0], adv, T, B, lda, TT, BT);
+    if (rc) return rc;
+    const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
+    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, omaps, dtab, value, ldv, static_cast<int>(T),
+                                                              static_cast<int>(B), gamma, factor);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
+template <int BT, int TT, int ST>
+static int launch_bwd_tma_st(const float* grad_adv, int64_t ldg, const float* dtab, float* gv, int64_t ldgv, float* gr,
+                             int64_t ldgr, int64_t T, int64_t B, float gamma, float factor, cudaStream_t stream) {
+    using Pipe = ScanPipeOut<1, 2, BT, TT, ST, 2>;
+    static SmemOptIn opt;
+    auto kernel = gae_bwd_tma_st<BT, TT, ST>;
+    if (int rc0 = opt.ensure(kernel, Pipe::kSmemBytes)) return rc0;
+    TmapPack<1> maps;
+    TmapPack<2> omaps;
+    int rc = make_tmap_2d(&maps.m[0], grad_adv, T, B, ldg, TT, BT);
+    if (rc) return rc;
+    rc = make_tmap_2d(&omaps.m[0], gv, T, B, ldgv, TT, BT);  // rows 0..T-1; row T is written by the kernel tail
+    if (rc) return rc;
+    rc = make_tmap_2d(&omaps.m[1], gr, T, B, ldgr, TT, BT);
+    if (rc) return rc;
+    const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
+    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, omaps, dtab, gv, ldgv, static_cast<int>(T),
+                                                              static_cast<int>(B), gamma, factor);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}
+
 // configuration table (index = hpc_rll_debug_set_config(HPC_RLL_OP_GAE, i)); -1/auto picks by B.
 //   0: BT=64  TT=16 ST=3      1: BT=128 TT=16 ST=3     2: BT=32 TT=32 ST=3
 //   3: BT=64  TT=32 ST=3      4: BT=128 TT=8  ST=4     5: BT=64 TT=8  ST=6
 //   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     8: BT=256 TT=16 ST=3
 //  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     13: BT=32 TT=64 ST=6   14: BT=32 TT=16 ST=12
 //  20: T-split (small batch; opt-in)   99: generic (non-TMA) kernel
+//  30..34: TMA-staged OUTPUT as well (ScanPipeOut; results leave as (TT x BT) bulk stores):
+//  30: BT=256 TT=8 ST=4    31: BT=128 TT=16 ST=3    32: BT=256 TT=16 ST=3    33: BT=256 TT=4 ST=6    34: BT=256 TT=4 ST=5
 // (a TMA box dimension is limited to 256 elements, so BT <= 256)
 // forced values >= 100 encode different kernels per direction: forward = v % 100, backward = v / 100
 static int pick_cfg(int64_t B, bool backward = false) {
@@ -509,7 +617,9 @@ static int pick_cfg(int64_t B, bool backward = false) {
     if (forced >= 100) forced = backward ? forced / 100 : forced % 100;
     if (forced >= 0) return forced;
     const int64_t sms = sm_count();
-    if (B >= 256 * sms) return 7;
+    // measured on B200 at T=1024, B=65536 (profiles/r01_gae_cfg_sweep_tma_store.md): bulk-store output with shallow
+    // boxes is 7-8 % faster than per-thread stores (forward 6.67 TB/s, backward 6.13 TB/s)
+    if (B >= 256 * sms) return backward ? 33 : 34;
     if (B >= 128 * sms) return 1;
     if (B >= 64 * sms) return 0;
     if (B >= 32 * sms) return 2;
@@ -606,6 +716,7 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
     int cfg = pick_cfg(B);
     const bool tma = tma_ok_2d(value, B, ldv) && tma_ok_2d(reward, B, ldr);
     if (!tma) cfg = 99;
+    if (cfg >= 30 && cfg < 99 && !tma_ok_2d(adv, B, lda)) cfg = 7;  // output not TMA-describable: per-thread stores
     switch (cfg) {
         case 0: return launch_fwd_tma<64, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         case 1: return launch_fwd_tma<128, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
@@ -620,6 +731,12 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
         case 11: return launch_fwd_tma<256, 8, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         case 13: return launch_fwd_tma<32, 64, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
         case 14: return launch_fwd_tma<32, 16, 12>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
+        // 30..: TMA-staged output (needs a TMA-describable adv as well)
+        case 30: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<256, 8, 4>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
+        case 31: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<128, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
+        case 32: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<256, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
+        case 33: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<256, 4, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
+        case 34: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<256, 4, 5>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
         default: break;
     }
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);
@@ -669,10 +786,10 @@ static int gae_forward_moments_impl(const float* value, const float* reward, flo
     if (!(tma_ok_2d(value, B, B) && tma_ok_2d(reward, B, B))) cfg = 99;
     int nblocks = 0;
     switch (cfg) {  // the tile shapes the automatic choice uses; anything else maps to the nearest of them
-        case 7: case 8: case 10: case 11:
+        case 7: case 8: case 10: case 11: case 30: case 32: case 33: case 34:
             rc = launch_fwd_tma<256, 8, 4, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
             break;
-        case 1: case 4: case 6:
+        case 1: case 4: case 6: case 31:
             rc = launch_fwd_tma<128, 16, 3, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
             break;
         case 0: case 3: case 5:
@@ -733,6 +850,7 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
     }
     int cfg = pick_cfg(B, true);
     if (!tma_ok_2d(grad_adv, B, ldg)) cfg = 99;
+    if (cfg >= 30 && cfg < 99 && !(tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr))) cfg = 7;
     switch (cfg) {
         case 0: return launch_bwd_tma<64, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         case 1: return launch_bwd_tma<128, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
@@ -747,6 +865,12 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
         case 11: return launch_bwd_tma<256, 8, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         case 13: return launch_bwd_tma<32, 64, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
         case 14: return launch_bwd_tma<32, 16, 12>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
+        // 30..: TMA-staged output (needs TMA-describable grad_value / grad_reward as well)
+        case 30: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<256, 8, 4>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
+        case 31: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<128, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
+        case 32: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<256, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
+        case 33: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<256, 4, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
+        case 34: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<256, 4, 5>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
         default: break;
     }
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);

@@ -26,4 +26,8 @@ out["copy_1r1w_gbs"] = 8 * n / t(lambda: y.copy_(x)) / 1e6
 out["fill_0r1w_gbs"] = 4 * n / t(lambda: y.zero_()) / 1e6
 out["sum_1r0w_gbs"] = 4 * n / t(lambda: x.sum()) / 1e6
 out["add_2r1w_gbs"] = 12 * n / t(lambda: torch.add(x, y, out=z)) / 1e6
+# 1 read : 2 writes, the mix of the GAE backward (grad_adv in; grad_value, grad_reward out): frexp is one
+# TensorIterator kernel with two outputs (fp32 mantissa + int32 exponent)
+mant, expo = torch.empty_like(x), torch.empty(n, dtype=torch.int32, device="cuda")
+out["frexp_1r2w_gbs"] = 12 * n / t(lambda: torch.frexp(x, out=(mant, expo))) / 1e6
 print(json.dumps(out))
