@@ -78,7 +78,7 @@ def test_gae_vs_golden(name):
     assert rel_err(gr, c.grad("reward", 64)) <= 1e-5
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 13, 14, 20, 30, 31, 32, 33, 99])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 13, 14, 20, 30, 31, 32, 33, 34, 99])
 def test_gae_every_kernel_config(cfg):
     """All tile configurations (and the non-TMA kernel) must give identical bits; 20 = T-split."""
     need_cuda()
