@@ -117,3 +117,15 @@ def test_product_never_touches_the_oracle():
                     txt = open(os.path.join(dirpath, f)).read()
                     assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, \
                         "%s references the oracle" % os.path.join(dirpath, f)
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/hpc_rll_b200.h must compile as C99 (no C++-isms, no torch types)."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "hpc_rll_b200.h")
+    r = subprocess.run(["/usr/bin/gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", hdr],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
+    txt = open(hdr).read()
+    assert "torch" not in re.sub(r"/\*.*?\*/", "", txt, flags=re.S), "no torch types in the C ABI"
+    assert 'extern "C"' in txt
