@@ -16,7 +16,8 @@ from tests._gpu import dev, host, need_cuda, rng
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1024, 64), (128, 128), (1, 5), (37, 3), (100, 260), (17, 1028), (64, 1), (33, 4), (250, 4096),
-          (16, 128), (15, 132), (1000, 7), (129, 2048), (513, 100), (2048, 36)]
+          (16, 128), (15, 132), (1000, 7), (129, 2048), (513, 100), (2048, 36),
+          (64, 65536), (7, 40000)]  # wide batches: the TMA-staged-output kernels (ragged T and column tiles)
 
 
 def uses_split(T, B):
