@@ -16,6 +16,9 @@
 // B200 design: ScanPipe (scan_pipe.cuh) -- (TT x BT) boxes of value/reward (fwd) or grad_adv (bwd)
 // plus the d_t slice are TMA-staged through a shared-memory ring; BT consumer threads own one
 // column each, carry (g, v_{t+1}) in registers and stream results out with evict-first stores.
+// From 256 columns per SM up the OUTPUT is TMA-staged as well (ScanPipeOut: results collected in shared-memory
+// boxes and written with cp.async.bulk.tensor stores; gae_*_tma_st, configs 30-34) -- 7-8 % faster at the
+// headline shape (profiles/r01_gae_cfg_sweep_tma_store.md).
 // HBM traffic = algorithmic: fwd 12 B/step, bwd 12 B/step (+ one extra value row).
 //
 // Arithmetic uses explicit round-to-nearest intrinsics in origin's operation order (no FMA
