@@ -129,3 +129,21 @@ def test_header_is_plain_c():
     txt = open(hdr).read()
     assert "torch" not in re.sub(r"/\*.*?\*/", "", txt, flags=re.S), "no torch types in the C ABI"
     assert 'extern "C"' in txt
+
+
+def test_di_engine_hpc_wrapper_lookup():
+    """DI-engine's ding/hpc_rl/wrapper.py resolves `hpc_rll.rl_utils.<module>.<Class>`, builds `cls(*shape).cuda()`
+    once per input shape and calls forward: every name it looks up must resolve and construct."""
+    import importlib
+    table = {"gae": ("gae", "GAE", (16, 8)), "td_lambda_error": ("td", "TDLambda", (16, 8)),
+             "dist_nstep_td_error": ("td", "DistNStepTD", (5, 8, 4, 51)), "q_nstep_td_error": ("td", "QNStepTD", (5, 8, 4)),
+             "q_nstep_td_error_with_rescale": ("td", "QNStepTDRescale", (5, 8, 4)),
+             "qrdqn_nstep_td_error": ("td", "QRDQNNStepTDError", (32, 5, 8, 4)),
+             "iqn_nstep_td_error": ("td", "IQNNStepTDError", (32, 32, 5, 8, 4)),
+             "upgo_loss": ("upgo", "UPGO", (16, 8, 4)), "vtrace_error": ("vtrace", "VTrace", (16, 8, 4)),
+             "ppo_error": ("ppo", "PPO", (8, 4))}
+    import torch
+    for fn_name, (mod, cls_name, shape) in table.items():
+        cls = getattr(importlib.import_module("hpc_rll.rl_utils." + mod), cls_name)
+        m = cls(*shape).cuda()  # parameter-free modules: .cuda() needs no device
+        assert isinstance(m, torch.nn.Module) and callable(m.forward), fn_name
