@@ -71,3 +71,14 @@ def test_sample_split_properties():
     L.hpc_rll_sample_split_group(shp.ctypes.data, len(shapes), 3, 4, 123, s1.ctypes.data, ctypes.byref(c1))
     L.hpc_rll_sample_split_group(shp.ctypes.data, len(shapes), 3, 4, 123, s2.ctypes.data, ctypes.byref(c2))
     assert c1.value == c2.value and np.array_equal(s1, s2)
+
+
+def test_staged_rows_index_division_is_exact():
+    """softmax_rows.cuh stage_rows/unstage_rows split a flat element index i < 256*32 into (row, col) with
+    row = floor((float(i) + 0.5f) * (1.0f / N)) instead of an integer division; exact for every N <= 32."""
+    import numpy as np
+    for N in range(1, 33):
+        inv = np.float32(1.0) / np.float32(N)
+        i = np.arange(256 * 32, dtype=np.int32)
+        row = np.floor((i.astype(np.float32) + np.float32(0.5)) * inv).astype(np.int32)
+        assert np.array_equal(row, i // N), N
