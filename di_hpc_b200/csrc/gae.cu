@@ -29,6 +29,7 @@
 // DESIGN.md); it costs 3 instructions instead of the ~14 of the generic IEEE division sequence.
 // Non-finite x yields NaN (IEEE division would give +-inf for x = +-inf).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -913,6 +914,12 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
     int64_t cb = (int64_t(2) << 20) / (T + 1);
     cb = (cb / 128) * 128;
     if (cb < 128) cb = 128;
+    // tuning knob (columns per block, multiple of 4): wider blocks = longer DMA rows, fewer pipeline stages
+    static const long long forced_cb = [] {
+        const char* e = getenv("HPC_RLL_HOST_BLOCK_COLS");
+        return e ? atoll(e) : 0LL;
+    }();
+    if (forced_cb >= 128) cb = (forced_cb / 4) * 4;
     if (cb > B) cb = ((B + 3) / 4) * 4;
     const size_t rows = static_cast<size_t>(T + 1);
     const size_t per_tensor = rows * static_cast<size_t>(cb);
