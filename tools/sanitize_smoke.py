@@ -6,7 +6,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from hpc_rll.rl_utils.gae import GAE  # noqa: E402
+from hpc_rll.rl_utils.gae import GAE, gae_with_adv_stats  # noqa: E402
 from hpc_rll.rl_utils.padding import Padding2D, UnPadding2D  # noqa: E402
 from hpc_rll.rl_utils.ppo import PPO  # noqa: E402
 from hpc_rll.rl_utils.td import (DistNStepTD, IQNNStepTDError, QNStepTD, QNStepTDRescale, QRDQNNStepTDError,  # noqa: E402
@@ -23,7 +23,32 @@ def r(*s):
     return torch.randn(*s, device=D)
 
 
+def wide_and_fused():
+    """kernels added late in round 1: TMA-staged output (ScanPipeOut, configs 30-34 = the default for wide batches),
+    GAE with moments + PPO with fused normalisation, 64-bit / staged row paths (N = 18 / 9)"""
+    T, B = 7, 40000
+    v, rew = r(T + 1, B).requires_grad_(True), r(T, B).requires_grad_(True)
+    for cfg in (-1, 30, 31, 32, 33, 34):
+        _abi.set_config(0, cfg)
+        torch.autograd.grad(GAE(T, B)(v, rew), [v, rew], grad_outputs=r(T, B))
+    _abi.set_config(0, -1)
+    adv, st = gae_with_adv_stats(v, rew)
+    R, N = T * B, 6
+    ln, vn = r(R, N).requires_grad_(True), r(R).requires_grad_(True)
+    l, _ = PPO(R, N)(ln, r(R, N), torch.randint(0, N, (R, ), device=D), vn, r(R), adv.reshape(-1), r(R), None, 0.2, True,
+                     None, adv_stats=st)
+    torch.autograd.grad(l.policy_loss + l.value_loss + l.entropy_loss, [ln, vn], grad_outputs=ONE)
+    for T, B, N in ((5, 300, 18), (5, 300, 9)):
+        t = r(T, B, N).requires_grad_(True)
+        a = torch.randint(0, N, (T, B), device=D)
+        v = r(T + 1, B).requires_grad_(True)
+        l = VTrace(T, B, N)(t, r(T, B, N), a, v, r(T, B), torch.rand(T, B, device=D))
+        torch.autograd.grad(l.policy_loss + l.value_loss + l.entropy_loss, [t, v], grad_outputs=ONE)
+        torch.autograd.grad(UPGO(T, B, N)(t, torch.rand(T, B, device=D), a, r(T, B), v.detach()), [t], grad_outputs=ONE)
+
+
 def main():
+    wide_and_fused()
     for T, B, N in ((37, 132, 6), (16, 260, 16), (9, 64, 40)):
         v, rew = r(T + 1, B).requires_grad_(True), r(T, B).requires_grad_(True)
         for cfg in (-1, 0, 2, 13, 20, 99):
