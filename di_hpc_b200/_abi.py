@@ -136,7 +136,8 @@ def require_i64_cuda(name: str, t: torch.Tensor) -> torch.Tensor:
 
 def workspace(op: int, T: int, B: int, N: int, device) -> torch.Tensor:
     """Allocate the scratch buffer an op asks for (torch caching allocator; stream-ordered reuse)."""
-    n = int(lib().hpc_rll_workspace_bytes(op, T, B, N))
+    with on_device(torch.device(device)):  # the size depends on the SM count of the tensor's device
+        n = int(lib().hpc_rll_workspace_bytes(op, T, B, N))
     return torch.empty(max(n, 8), dtype=torch.uint8, device=device)
 
 

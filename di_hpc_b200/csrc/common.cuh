@@ -60,18 +60,22 @@ bool tma_ok_2d(const void* base, int64_t cols, int64_t ld);
 int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                  int box_cols);
 
-// Opt a kernel into > 48 KB dynamic shared memory, once per device (the attribute is per context).
+// Opt a kernel into > 48 KB dynamic shared memory.  The attribute is per context and holds the LARGEST byte count
+// granted so far per device: kernels whose dynamic size varies at run time (n_atom / tau dependent, nstep.cu) are
+// re-opted whenever a call needs more than any earlier one (a first call at ~50 KB used to pin the limit).
 struct SmemOptIn {
-    bool done[64] = {};
+    int granted[64] = {};
     template <typename K>
     int ensure(K kernel, int bytes) {
         int dev = 0;
         HPC_CUDA(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && done[dev]) return HPC_RLL_OK;
+        const bool tracked = dev >= 0 && dev < 64;
+        if (tracked && granted[dev] >= bytes && granted[dev] > 0) return HPC_RLL_OK;
         HPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        HPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                      cudaSharedmemCarveoutMaxShared));
-        if (dev >= 0 && dev < 64) done[dev] = true;
+        if (!tracked || granted[dev] == 0)
+            HPC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          cudaSharedmemCarveoutMaxShared));
+        if (tracked) granted[dev] = bytes;
         return HPC_RLL_OK;
     }
 };

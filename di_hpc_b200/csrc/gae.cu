@@ -58,11 +58,27 @@ struct DtabKey {
     }
 };
 std::mutex g_dtab_mu;
-std::map<DtabKey, float*> g_dtab;
+struct DtabEntry {
+    float* ptr;
+    uint64_t last_use;
+};
+std::map<DtabKey, DtabEntry> g_dtab;
+uint64_t g_dtab_tick = 0;
 constexpr int kDtabPad = 64;
+constexpr size_t kDtabMaxPerDevice = 1024;  // tables are 8*(T+128) bytes each
 }  // namespace
 
-static int get_dtab(int64_t T, double lambda, const float** out) {
+static bool stream_capturing(cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+}
+
+// Cache policy: bounded PER DEVICE; when a device's share is full the least recently used table OF
+// THAT DEVICE is dropped after synchronising that device (the current one -- other devices' tables and streams
+// are never touched).  Nothing is freed while `stream` is being captured (a synchronise would invalidate the
+// capture); a table pointer baked into an instantiated graph stays valid as long as its (T, lambda) is among the
+// 1024 most recently used on that device.
+static int get_dtab(int64_t T, double lambda, cudaStream_t stream, const float** out) {
     int dev = 0;
     HPC_CUDA(cudaGetDevice(&dev));
     DtabKey key{dev, T, 0};
@@ -70,13 +86,21 @@ static int get_dtab(int64_t T, double lambda, const float** out) {
     std::lock_guard<std::mutex> lk(g_dtab_mu);
     auto it = g_dtab.find(key);
     if (it != g_dtab.end()) {
-        *out = it->second;
+        it->second.last_use = ++g_dtab_tick;
+        *out = it->second.ptr;
         return HPC_RLL_OK;
     }
-    if (g_dtab.size() >= 256) {  // rare: bound the cache; entries may still be in use -> drain first
-        HPC_CUDA(cudaDeviceSynchronize());
-        for (auto& kv : g_dtab) cudaFree(kv.second);
-        g_dtab.clear();
+    size_t mine = 0;
+    auto lru = g_dtab.end();
+    for (auto i = g_dtab.begin(); i != g_dtab.end(); ++i) {
+        if (i->first.dev != dev) continue;
+        ++mine;
+        if (lru == g_dtab.end() || i->second.last_use < lru->second.last_use) lru = i;
+    }
+    if (mine >= kDtabMaxPerDevice && lru != g_dtab.end() && !stream_capturing(stream)) {
+        HPC_CUDA(cudaDeviceSynchronize());  // this device only; its kernels may still read the table
+        cudaFree(lru->second.ptr);
+        g_dtab.erase(lru);
     }
     const int64_t padded = ((T + kDtabPad - 1) / kDtabPad) * kDtabPad + kDtabPad;
     std::vector<float> h(static_cast<size_t>(padded) * 2, 1.0f);
@@ -96,7 +120,7 @@ static int get_dtab(int64_t T, double lambda, const float** out) {
         cudaFree(d);
         return set_error(HPC_RLL_ECUDA, "gae: uploading d_t table failed: %s", cudaGetErrorString(e));
     }
-    g_dtab[key] = d;
+    g_dtab[key] = DtabEntry{d, ++g_dtab_tick};
     *out = d;
     return HPC_RLL_OK;
 }
@@ -665,10 +689,6 @@ std::map<int, SplitScratch> g_split;
 
 // inside CUDA-graph capture the cross-stream event handshake is skipped (a graph replays on one stream
 // in order; warm up once before capturing so the scratch exists)
-static bool stream_capturing(cudaStream_t stream) {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    return cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
-}
 
 static int split_scratch(size_t floats, cudaStream_t stream, SplitScratch** out) {
     int dev = 0;
@@ -699,7 +719,7 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
     HPC_REQUIRE(ldv >= B && ldr >= B && lda >= B, "gae_forward: row pitch smaller than B");
     HPC_REQUIRE(T < (int64_t(1) << 31) - 64 && B < (int64_t(1) << 31) - 512, "gae_forward: T/B exceed 2^31");
     const float* dtab = nullptr;
-    int rc = get_dtab(T, lambda, &dtab);
+    int rc = get_dtab(T, lambda, stream, &dtab);
     if (rc) return rc;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
     int S = 0, seg_len = 0;
@@ -783,7 +803,7 @@ size_t gae_moments_workspace_bytes(int64_t B) { return 2 * sizeof(double) * stat
 static int gae_forward_moments_impl(const float* value, const float* reward, float* adv, double* moments, int64_t T,
                                     int64_t B, double gamma, double lambda, double* partials, cudaStream_t stream) {
     const float* dtab = nullptr;
-    int rc = get_dtab(T, lambda, &dtab);
+    int rc = get_dtab(T, lambda, stream, &dtab);
     if (rc) return rc;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
     int cfg = pick_cfg(B);
@@ -834,7 +854,7 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
     HPC_REQUIRE(ldg >= B && ldgv >= B && ldgr >= B, "gae_backward: row pitch smaller than B");
     HPC_REQUIRE(T < (int64_t(1) << 31) - 64 && B < (int64_t(1) << 31) - 512, "gae_backward: T/B exceed 2^31");
     const float* dtab = nullptr;
-    int rc = get_dtab(T, lambda, &dtab);
+    int rc = get_dtab(T, lambda, stream, &dtab);
     if (rc) return rc;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
     int S = 0, seg_len = 0;

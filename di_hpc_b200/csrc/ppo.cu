@@ -302,7 +302,7 @@ static int ppo_forward_impl(const float* logits_new, const float* logits_old, co
                                                  weight, pol_coef, val_coef, partials, P, B, n, ge.G, log2G)
     if (staged) {
         static SmemOptIn opt;
-        if (int rc0 = opt.ensure(ppo_rows_fwd_staged, static_cast<int>(stage_bytes(31, 2)))) return rc0;  // largest pitch
+        if (int rc0 = opt.ensure(ppo_rows_fwd_staged, static_cast<int>(stage_bytes(32, 2)))) return rc0;  // largest pitch (N=32 -> 33)
         ppo_rows_fwd_staged<<<grid, kStageRows, stage_bytes(n, 2), stream>>>(
             logits_new, logits_old, action, value_new, value_old, adv, return_, weight, pol_coef, val_coef, partials, P, B,
             n, stage_pitch(n), aligned16(logits_new) && aligned16(logits_old) ? 1 : 0);

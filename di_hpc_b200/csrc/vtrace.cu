@@ -364,7 +364,7 @@ int hpc_rll_vtrace_forward(const float* target_output, const float* behaviour_ou
                                                      logp_buf, partials, R, n, ge.G, log2G)
     if (staged) {
         static SmemOptIn opt;
-        if (int rc0 = opt.ensure(vtrace_rows_fwd_staged, static_cast<int>(stage_bytes(31, 2)))) return rc0;  // largest pitch
+        if (int rc0 = opt.ensure(vtrace_rows_fwd_staged, static_cast<int>(stage_bytes(32, 2)))) return rc0;  // largest pitch (N=32 -> 33)
         vtrace_rows_fwd_staged<<<grid1, kStageRows, stage_bytes(n, 2), stream>>>(
             target_output, behaviour_output, action, weight, is_buf, logp_buf, partials, R, n, stage_pitch(n),
             aligned16(target_output) && aligned16(behaviour_output) ? 1 : 0);

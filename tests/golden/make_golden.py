@@ -317,6 +317,113 @@ def case_padding(name, ndim, n, lo_hi, value, group, seed):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **blob)
 
 
+
+# ----------------------------------------------------------------------------- exact-tie fixtures
+# Inputs constructed so that the comparisons with tie semantics are hit EXACTLY:
+#   origin/td.py:512-515 (QR-DQN Huber `<1`, `le(0.)`), origin/td.py:433,443 (IQN `abs()<=kappa`, `err<0`),
+#   origin/upgo.py:36 (`>=`), origin/ppo.py:62-76 (torch.min / torch.max / clamp).
+def _int_tensor(g, shape, lo, hi):
+    return torch.randint(lo, hi + 1, shape, generator=g).float()
+
+
+def case_qrdqn_tie(name, tau, T, B, N, use_weight, seed):
+    """integer-valued q / next_n_q / reward, gamma = 1, value_gamma = None (= gamma**T = 1): every pairwise error
+    is an integer, so err == 0 (the `le(0.)` side) and |err| == 1 (the Huber `<1` boundary) occur in bulk."""
+    g = gen(seed)
+    inputs = dict(q=_int_tensor(g, (B, N, tau), -2, 2), next_n_q=_int_tensor(g, (B, N, tau), -2, 2),
+                  action=torch.randint(0, N, (B,), generator=g), next_n_action=torch.randint(0, N, (B,), generator=g),
+                  reward=_int_tensor(g, (T, B), -1, 1), done=(torch.rand(B, generator=g) < 0.3).float(),
+                  weight=_int_tensor(g, (B,), 1, 3) if use_weight else None, value_gamma=None)
+
+    def fn(c):
+        loss, td = O.td.qrdqn_nstep_td_error(
+            O.td.qrdqn_nstep_td_data(c["q"], c["next_n_q"], c["action"], c["next_n_action"], c["reward"], c["done"],
+                                     tau, c["weight"]), 1.0, T, c["value_gamma"])
+        return dict(loss=loss, td_error_per_sample=td), 1.0 * loss
+
+    save_case(name, fn, inputs, ["q"], dict(gamma=1.0, tau=tau, coef_loss=1.0))
+
+
+def case_iqn_tie(name, tau, tau_p, T, B, N, kappa, seed):
+    """integer-valued inputs, gamma = 1: errors are integers, so |err| == kappa (inclusive quadratic branch,
+    origin/td.py:433) and err == 0 (`err < 0` is false there, origin/td.py:443) are both hit; replay quantiles
+    are multiples of 1/4 so the quantile weights are exact too."""
+    g = gen(seed)
+    inputs = dict(q=_int_tensor(g, (tau, B, N), -2, 2), next_n_q=_int_tensor(g, (tau_p, B, N), -2, 2),
+                  action=torch.randint(0, N, (B,), generator=g), next_n_action=torch.randint(0, N, (B,), generator=g),
+                  reward=_int_tensor(g, (T, B), -1, 1), done=(torch.rand(B, generator=g) < 0.3).float(),
+                  replay_quantiles=_int_tensor(g, (tau, B), 0, 4) / 4.0, weight=None, value_gamma=None)
+
+    def fn(c):
+        loss, td = O.td.iqn_nstep_td_error(
+            O.td.iqn_nstep_td_data(c["q"], c["next_n_q"], c["action"], c["next_n_action"], c["reward"], c["done"],
+                                   c["replay_quantiles"], c["weight"]), 1.0, T, kappa, c["value_gamma"])
+        return dict(loss=loss, td_error_per_sample=td), 1.0 * loss
+
+    save_case(name, fn, inputs, ["q"], dict(gamma=1.0, kappa=kappa, coef_loss=1.0))
+
+
+def case_upgo_tie(name, T, B, N, seed):
+    """integer rewards / bootstrap values: r[t+1] + v[t+2] == v[t+1] happens on about a third of the steps, where
+    origin's `>=` (upgo.py:36) keeps following the trajectory; rhos are powers of two."""
+    g = gen(seed)
+    inputs = dict(target_output=torch.randn(T, B, N, generator=g) * 1.5,
+                  rhos=torch.tensor([0.5, 1.0, 2.0])[torch.randint(0, 3, (T, B), generator=g)],
+                  action=torch.randint(0, N, (T, B), generator=g), rewards=_int_tensor(g, (T, B), -1, 1),
+                  bootstrap_values=_int_tensor(g, (T + 1, B), -1, 1))
+
+    def fn(c):
+        loss = O.upgo.upgo_loss(c["target_output"], c["rhos"], c["action"], c["rewards"], c["bootstrap_values"])
+        with torch.no_grad():
+            ret = O.upgo.upgo_returns(c["rewards"], c["bootstrap_values"])
+        return dict(loss=loss, ret=ret), 1.0 * loss
+
+    save_case(name, fn, inputs, ["target_output"], dict(coef_loss=1.0))
+
+
+def case_ppo_tie(name, B, N, clip_ratio, use_value_clip, dual_clip, seed):
+    """Every PPO tie at once (origin/ppo.py:62-76):
+      * logits_new == logits_old            -> ratio == 1 exactly, surr1 == surr2 (torch.min tie)
+      * adv == 0 on a third of the samples  -> surr1 == surr2 == dual_clip*adv == 0 (torch.max tie of the dual clip)
+      * value clip: v_new=.5, v_old=0, eps=.25, ret=.375 -> (ret-v)^2 == (ret-v_clip)^2 == 1/64 (torch.max tie:
+        autograd splits the gradient, half of it reaches v_new) on every other sample."""
+    g = gen(seed)
+    logit = torch.randn(B, N, generator=g)
+    adv = _int_tensor(g, (B,), -1, 1)
+    vn = torch.randn(B, generator=g)
+    vo = torch.randn(B, generator=g)
+    ret = torch.randn(B, generator=g)
+    vn[::2], vo[::2], ret[::2] = 0.5, 0.0, 0.375
+    inputs = dict(logits_new=logit.clone(), logits_old=logit, action=torch.randint(0, N, (B,), generator=g),
+                  value_new=vn, value_old=vo, adv=adv, return_=ret, weight=None)
+    coef = (1.0, 1.0, -0.5)
+
+    def fn(c):
+        l, info = O.ppo.ppo_error(O.ppo.ppo_data(c["logits_new"], c["logits_old"], c["action"], c["value_new"],
+                                                 c["value_old"], c["adv"], c["return_"], c["weight"]),
+                                  clip_ratio, use_value_clip, dual_clip)
+        outs = dict(policy_loss=l.policy_loss, value_loss=l.value_loss, entropy_loss=l.entropy_loss,
+                    approx_kl=torch.tensor(info.approx_kl), clipfrac=torch.tensor(info.clipfrac))
+        return outs, coef[0] * l.policy_loss + coef[1] * l.value_loss + coef[2] * l.entropy_loss
+
+    save_case(name, fn, inputs, ["logits_new", "value_new"],
+              dict(clip_ratio=clip_ratio, use_value_clip=float(use_value_clip), dual_clip=dual_clip,
+                   coef_policy=coef[0], coef_value=coef[1], coef_entropy=coef[2]))
+
+
+def main_ties():
+    s = 4321
+    case_qrdqn_tie("qrdqn_tie_tau16_t3_b12_n3", 16, 3, 12, 3, False, s + 1)
+    case_qrdqn_tie("qrdqn_tie_tau64_t5_b6_n2_w", 64, 5, 6, 2, True, s + 2)
+    case_iqn_tie("iqn_tie_tau16_16_t3_b12_n3_k1", 16, 16, 3, 12, 3, 1.0, s + 3)
+    case_iqn_tie("iqn_tie_tau33_20_t2_b7_n2_k2", 33, 20, 2, 7, 2, 2.0, s + 4)
+    case_upgo_tie("upgo_tie_t24_b9_n5", 24, 9, 5, s + 5)
+    case_upgo_tie("upgo_tie_t7_b33_n16", 7, 33, 16, s + 6)
+    case_ppo_tie("ppo_tie_b24_n6_vclip", 24, 6, 0.25, True, None, s + 7)
+    case_ppo_tie("ppo_tie_b24_n16_vclip_dual", 24, 16, 0.25, True, 2.0, s + 8)
+    case_ppo_tie("ppo_tie_b10_n3_noclip_dual", 10, 3, 0.25, False, 3.0, s + 9)
+
+
 def main_gae_ppo():
     s = 1234
     case_gae_ppo("gaeppo_t16_b8_n6", 16, 8, 6, False, 0.2, True, None, s + 100)
@@ -327,10 +434,13 @@ def main_gae_ppo():
 def main():
     if sys.argv[1:] == ["gaeppo"]:  # add the chain fixtures without re-zipping the others
         return main_gae_ppo()
+    if sys.argv[1:] == ["ties"]:  # add the exact-tie fixtures without re-zipping the others
+        return main_ties()
     for f in os.listdir(HERE):
         if f.endswith(".npz"):
             os.remove(os.path.join(HERE, f))
     main_gae_ppo()
+    main_ties()
     s = 1234
     case_gae("gae_t16_b8", 16, 8, 0.99, 0.97, s + 1)
     case_gae("gae_t1_b5", 1, 5, 0.99, 0.97, s + 2)

@@ -107,3 +107,39 @@ def test_vtrace_upgo_c2_column_subset_vs_oracle():
     o = orc.upgo(host(tgt[:, cols]), host(rhos[:, cols]), host(action[:, cols]), host(reward[:, cols]),
                  host(value[:, cols]))
     close(host(tgt.grad[:, cols]) * (B / S), o["grad_target_output"], "upgo grad_target_output")
+
+
+def test_vtrace_upgo_c2_full_losses_vs_oracle():
+    """The whole C2 problem (T=512, B=32768, N=16: 16.8 M steps) through the C oracle: the three V-trace losses
+    and the UPGO loss at full size -- the column-subset test above only sees gradients -- plus the complete
+    gradient tensors.  ~15 s of host time (oracle is C + OpenMP)."""
+    need_cuda()
+    from hpc_rll.rl_utils.upgo import UPGO
+    from hpc_rll.rl_utils.vtrace import VTrace
+    T, B, N = 512, 32768, 16
+    g = gen(35)
+    tgt = torch.randn(T, B, N, device="cuda", generator=g).requires_grad_(True)
+    beh = torch.randn(T, B, N, device="cuda", generator=g)
+    action = torch.randint(0, N, (T, B), device="cuda", generator=g)
+    value = torch.randn(T + 1, B, device="cuda", generator=g).requires_grad_(True)
+    reward = torch.randn(T, B, device="cuda", generator=g)
+    weight = torch.rand(T, B, device="cuda", generator=g)
+    coef = [1.0, 0.5, -0.25]
+    l = VTrace(T, B, N)(tgt, beh, action, value, reward, weight)
+    (coef[0] * l.policy_loss + coef[1] * l.value_loss + coef[2] * l.entropy_loss).sum().backward()
+    o = orc.vtrace(host(tgt), host(beh), host(action), host(value), host(reward), host(weight), coef=coef)
+    for got, name in zip(l, ("policy_loss", "value_loss", "entropy_loss")):
+        want = float(o[name])
+        assert abs(float(got.item()) - want) <= TOL * max(1.0, abs(want)), (name, float(got.item()), want)
+    n = float(T * B)  # gradients carry 1/(T*B): compare them at O(1) scale, or the norm-relative bar is vacuous
+    close(host(tgt.grad * n), o["grad_target_output"] * np.float32(n), "vtrace grad_target_output (full)")
+    close(host(value.grad * n), o["grad_value"] * np.float32(n), "vtrace grad_value (full)")
+    del o
+    tgt.grad = None
+    rhos = torch.rand(T, B, device="cuda", generator=g) * 2
+    loss = UPGO(T, B, N)(tgt, rhos, action, reward, value.detach())
+    loss.sum().backward()
+    o = orc.upgo(host(tgt), host(rhos), host(action), host(reward), host(value))
+    want = float(o["loss"])
+    assert abs(float(loss.item()) - want) <= TOL * max(1.0, abs(want)), (float(loss.item()), want)
+    close(host(tgt.grad * n), o["grad_target_output"] * np.float32(n), "upgo grad_target_output (full)")
