@@ -181,9 +181,11 @@ __device__ __forceinline__ void gae_store_moments(const GaeFwdBody<MOM>& body, d
 template <int BT, int TT, int ST, bool MOM>
 __global__ void __launch_bounds__(BT + 32) gae_fwd_tma(const __grid_constant__ TmapPack<2> maps,
                                                         const float* __restrict__ dtab,
-                                                        const float* __restrict__ value, int64_t ld_value,
+                                                        const float* __restrict__ v_next, float* __restrict__ carry,
                                                         float* __restrict__ adv, int64_t ld_adv, int T, int B,
                                                         float gamma, float factor, double* __restrict__ partials) {
+    // v_next: the value row that follows the last row of this launch (value[T], or the carried row of a T-chunk);
+    // carry (nullable): (2,B) scan state of a T-chunked run -- g in/out, value row out (see gae_forward_chunk)
     using Pipe = ScanPipe<2, BT, TT, ST, 2>;
     const int col0 = blockIdx.x * BT;
     const int col = col0 + threadIdx.x;
@@ -198,8 +200,13 @@ __global__ void __launch_bounds__(BT + 32) gae_fwd_tma(const __grid_constant__ T
     body.p1 = 0.f;
     body.p2 = 0.f;
     body.adv = adv + static_cast<int64_t>(T - 1) * ld_adv + col;
-    body.v1 = body.valid ? __ldg(value + static_cast<int64_t>(T) * ld_value + col) : 0.f;
+    body.v1 = body.valid ? v_next[col] : 0.f;
+    if (carry != nullptr && body.valid) body.g = carry[col];
     Pipe::template run<true>(maps, dtab, T, col0, body);
+    if (carry != nullptr && body.valid) {
+        carry[col] = body.g;
+        carry[B + col] = body.v1;
+    }
     if constexpr (MOM) {
         __shared__ double red[64];
         gae_store_moments<MOM>(body, partials, red);
@@ -232,7 +239,10 @@ __global__ void __launch_bounds__(BT + 32) gae_bwd_tma(const __grid_constant__ T
                                                         const float* __restrict__ dtab,
                                                         float* __restrict__ grad_value, int64_t ld_gv,
                                                         float* __restrict__ grad_reward, int64_t ld_gr, int T, int B,
-                                                        float gamma, float factor) {
+                                                        float gamma, float factor, float* __restrict__ carry,
+                                                        int write_last) {
+    // carry (nullable): (2,B) = (ghat, dd of the previous row) of a T-chunked run; write_last: this launch ends at the
+    // global row T-1, so row T of grad_value (= gamma*dd_{T-1}) is written as well
     using Pipe = ScanPipe<1, BT, TT, ST, 2>;
     const int col0 = blockIdx.x * BT;
     const int col = col0 + threadIdx.x;
@@ -246,8 +256,16 @@ __global__ void __launch_bounds__(BT + 32) gae_bwd_tma(const __grid_constant__ T
     body.gr = grad_reward + col;
     body.ld_gv = ld_gv;
     body.ld_gr = ld_gr;
+    if (carry != nullptr && body.valid) {
+        body.gh = carry[col];
+        body.prev = carry[B + col];
+    }
     Pipe::template run<false>(maps, dtab, T, col0, body);
-    if (body.valid) st_stream(body.gv, __fmul_rn(gamma, body.prev));  // row T
+    if (body.valid && write_last) st_stream(body.gv, __fmul_rn(gamma, body.prev));  // row T
+    if (carry != nullptr && body.valid) {
+        carry[col] = body.gh;
+        carry[B + col] = body.prev;
+    }
 }
 
 // ---- variants with TMA-staged OUTPUT (ScanPipeOut): same arithmetic, results leave as (TT x BT) bulk stores ----
@@ -265,17 +283,23 @@ template <int BT, int TT, int ST>
 __global__ void __launch_bounds__(BT + 32) gae_fwd_tma_st(const __grid_constant__ TmapPack<2> maps,
                                                            const __grid_constant__ TmapPack<1> omaps,
                                                            const float* __restrict__ dtab,
-                                                           const float* __restrict__ value, int64_t ld_value, int T,
-                                                           int B, float gamma, float factor) {
+                                                           const float* __restrict__ v_next,
+                                                           float* __restrict__ carry, int T, int B, float gamma,
+                                                           float factor) {
     using Pipe = ScanPipeOut<2, 1, BT, TT, ST, 2>;
     const int col0 = blockIdx.x * BT;
     const int col = col0 + threadIdx.x;
+    const bool valid = threadIdx.x < BT && col < B;
     GaeFwdBodyO body;
-    body.g = 0.f;
+    body.g = (carry != nullptr && valid) ? carry[col] : 0.f;
     body.gamma = gamma;
     body.factor = factor;
-    body.v1 = (threadIdx.x < BT && col < B) ? __ldg(value + static_cast<int64_t>(T) * ld_value + col) : 0.f;
+    body.v1 = valid ? v_next[col] : 0.f;
     Pipe::template run<true>(maps, omaps, dtab, T, col0, body);
+    if (carry != nullptr && valid) {
+        carry[col] = body.g;
+        carry[B + col] = body.v1;
+    }
 }
 
 struct GaeBwdBodyO {
@@ -295,18 +319,24 @@ __global__ void __launch_bounds__(BT + 32) gae_bwd_tma_st(const __grid_constant_
                                                            const __grid_constant__ TmapPack<2> omaps,
                                                            const float* __restrict__ dtab,
                                                            float* __restrict__ grad_value, int64_t ld_gv, int T, int B,
-                                                           float gamma, float factor) {
+                                                           float gamma, float factor, float* __restrict__ carry,
+                                                           int write_last) {
     using Pipe = ScanPipeOut<1, 2, BT, TT, ST, 2>;
     const int col0 = blockIdx.x * BT;
     const int col = col0 + threadIdx.x;
+    const bool valid = threadIdx.x < BT && col < B;
     GaeBwdBodyO body;
-    body.gh = 0.f;
-    body.prev = 0.f;
+    body.gh = (carry != nullptr && valid) ? carry[col] : 0.f;
+    body.prev = (carry != nullptr && valid) ? carry[B + col] : 0.f;
     body.gamma = gamma;
     body.factor = factor;
     Pipe::template run<false>(maps, omaps, dtab, T, col0, body);
     // row T of grad_value is outside the output tensor map (T rows): one plain store per column
-    if (threadIdx.x < BT && col < B) st_stream(grad_value + static_cast<int64_t>(T) * ld_gv + col, __fmul_rn(gamma, body.prev));
+    if (valid && write_last) st_stream(grad_value + static_cast<int64_t>(T) * ld_gv + col, __fmul_rn(gamma, body.prev));
+    if (carry != nullptr && valid) {
+        carry[col] = body.gh;
+        carry[B + col] = body.prev;
+    }
 }
 
 // Generic (no alignment requirements) variants: one thread per column, plain coalesced loads with
@@ -317,7 +347,8 @@ __global__ void __launch_bounds__(128) gae_fwd_generic(const float* __restrict__
                                                         const float* __restrict__ reward, int64_t ld_reward,
                                                         const float* __restrict__ dtab, float* __restrict__ adv,
                                                         int64_t ld_adv, int T, int B, float gamma, float factor,
-                                                        double* __restrict__ partials) {
+                                                        double* __restrict__ partials,
+                                                        const float* __restrict__ v_next, float* __restrict__ carry) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     GaeFwdBody<MOM> body;
     body.valid = col < B;
@@ -332,7 +363,8 @@ __global__ void __launch_bounds__(128) gae_fwd_generic(const float* __restrict__
         body.factor = factor;
         body.ld = ld_adv;
         body.adv = adv + static_cast<int64_t>(T - 1) * ld_adv + col;
-        body.v1 = value[static_cast<int64_t>(T) * ld_value + col];
+        body.v1 = v_next[col];
+        if (carry != nullptr) body.g = carry[col];
         constexpr int U = 8;
         int t = T - 1;
         for (; t >= U - 1; t -= U) {
@@ -358,6 +390,10 @@ __global__ void __launch_bounds__(128) gae_fwd_generic(const float* __restrict__
             const float dt[2] = {d.x, d.y};
             body.step(t, x, dt);
         }
+        if (carry != nullptr) {
+            carry[col] = body.g;
+            carry[B + col] = body.v1;
+        }
     }
     if constexpr (MOM) {
         __shared__ double red[64];
@@ -369,13 +405,14 @@ __global__ void __launch_bounds__(128) gae_bwd_generic(const float* __restrict__
                                                         const float* __restrict__ dtab,
                                                         float* __restrict__ grad_value, int64_t ld_gv,
                                                         float* __restrict__ grad_reward, int64_t ld_gr, int T, int B,
-                                                        float gamma, float factor) {
+                                                        float gamma, float factor, float* __restrict__ carry,
+                                                        int write_last) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= B) return;
     GaeBwdBody body;
     body.valid = true;
-    body.gh = 0.f;
-    body.prev = 0.f;
+    body.gh = carry != nullptr ? carry[col] : 0.f;
+    body.prev = carry != nullptr ? carry[B + col] : 0.f;
     body.gamma = gamma;
     body.factor = factor;
     body.gv = grad_value + col;
@@ -405,7 +442,11 @@ __global__ void __launch_bounds__(128) gae_bwd_generic(const float* __restrict__
         const float dt[2] = {d.x, d.y};
         body.step(t, x, dt);
     }
-    *body.gv = __fmul_rn(gamma, body.prev);  // row T
+    if (write_last) *body.gv = __fmul_rn(gamma, body.prev);  // row T
+    if (carry != nullptr) {
+        carry[col] = body.gh;
+        carry[B + col] = body.prev;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -546,7 +587,8 @@ __global__ void __launch_bounds__(kSplitThreads) gae_bwd_split(const float* __re
 template <int BT, int TT, int ST, bool MOM = false>
 static int launch_fwd_tma(const float* value, int64_t ldv, const float* reward, int64_t ldr, const float* dtab,
                           float* adv, int64_t lda, int64_t T, int64_t B, float gamma, float factor,
-                          cudaStream_t stream, double* partials = nullptr, int* nblocks = nullptr) {
+                          cudaStream_t stream, double* partials = nullptr, int* nblocks = nullptr,
+                          const float* v_next = nullptr, float* carry = nullptr) {
     using Pipe = ScanPipe<2, BT, TT, ST, 2>;
     static SmemOptIn opt;
     auto kernel = gae_fwd_tma<BT, TT, ST, MOM>;
@@ -558,7 +600,8 @@ static int launch_fwd_tma(const float* value, int64_t ldv, const float* reward, 
     if (rc) return rc;
     const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
     if (nblocks) *nblocks = static_cast<int>(grid);
-    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, dtab, value, ldv, adv, lda, static_cast<int>(T),
+    if (v_next == nullptr) v_next = value + T * ldv;
+    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, dtab, v_next, carry, adv, lda, static_cast<int>(T),
                                                               static_cast<int>(B), gamma, factor, partials);
     count_launch();
     HPC_LAUNCH_CHECK();
@@ -567,7 +610,8 @@ static int launch_fwd_tma(const float* value, int64_t ldv, const float* reward, 
 
 template <int BT, int TT, int ST>
 static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab, float* gv, int64_t ldgv, float* gr,
-                          int64_t ldgr, int64_t T, int64_t B, float gamma, float factor, cudaStream_t stream) {
+                          int64_t ldgr, int64_t T, int64_t B, float gamma, float factor, cudaStream_t stream,
+                          float* carry = nullptr, int write_last = 1) {
     using Pipe = ScanPipe<1, BT, TT, ST, 2>;
     static SmemOptIn opt;
     auto kernel = gae_bwd_tma<BT, TT, ST>;
@@ -577,7 +621,7 @@ static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab,
     if (rc) return rc;
     const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
     kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, dtab, gv, ldgv, gr, ldgr, static_cast<int>(T),
-                                                              static_cast<int>(B), gamma, factor);
+                                                              static_cast<int>(B), gamma, factor, carry, write_last);
     count_launch();
     HPC_LAUNCH_CHECK();
     return HPC_RLL_OK;
@@ -586,7 +630,7 @@ static int launch_bwd_tma(const float* grad_adv, int64_t ldg, const float* dtab,
 template <int BT, int TT, int ST>
 static int launch_fwd_tma_st(const float* value, int64_t ldv, const float* reward, int64_t ldr, const float* dtab,
                              float* adv, int64_t lda, int64_t T, int64_t B, float gamma, float factor,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, const float* v_next = nullptr, float* carry = nullptr) {
     using Pipe = ScanPipeOut<2, 1, BT, TT, ST, 2>;
     static SmemOptIn opt;
     auto kernel = gae_fwd_tma_st<BT, TT, ST>;
@@ -600,7 +644,8 @@ static int launch_fwd_tma_st(const float* value, int64_t ldv, const float* rewar
     rc = make_tmap_2d(&omaps.m[0], adv, T, B, lda, TT, BT);
     if (rc) return rc;
     const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
-    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, omaps, dtab, value, ldv, static_cast<int>(T),
+    if (v_next == nullptr) v_next = value + T * ldv;
+    kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, omaps, dtab, v_next, carry, static_cast<int>(T),
                                                               static_cast<int>(B), gamma, factor);
     count_launch();
     HPC_LAUNCH_CHECK();
@@ -609,7 +654,8 @@ static int launch_fwd_tma_st(const float* value, int64_t ldv, const float* rewar
 
 template <int BT, int TT, int ST>
 static int launch_bwd_tma_st(const float* grad_adv, int64_t ldg, const float* dtab, float* gv, int64_t ldgv, float* gr,
-                             int64_t ldgr, int64_t T, int64_t B, float gamma, float factor, cudaStream_t stream) {
+                             int64_t ldgr, int64_t T, int64_t B, float gamma, float factor, cudaStream_t stream,
+                             float* carry = nullptr, int write_last = 1) {
     using Pipe = ScanPipeOut<1, 2, BT, TT, ST, 2>;
     static SmemOptIn opt;
     auto kernel = gae_bwd_tma_st<BT, TT, ST>;
@@ -624,7 +670,7 @@ static int launch_bwd_tma_st(const float* grad_adv, int64_t ldg, const float* dt
     if (rc) return rc;
     const unsigned grid = static_cast<unsigned>((B + BT - 1) / BT);
     kernel<<<grid, Pipe::kThreads, Pipe::kSmemBytes, stream>>>(maps, omaps, dtab, gv, ldgv, static_cast<int>(T),
-                                                              static_cast<int>(B), gamma, factor);
+                                                              static_cast<int>(B), gamma, factor, carry, write_last);
     count_launch();
     HPC_LAUNCH_CHECK();
     return HPC_RLL_OK;
@@ -711,19 +757,32 @@ static int split_scratch(size_t floats, cudaStream_t stream, SplitScratch** out)
     return HPC_RLL_OK;
 }
 
+// One launch of the forward scan over `T` consecutive rows.  A whole problem has chunk == nullptr; a T-chunk of a
+// longer trajectory (rows [t0, t0+T) of T_total) passes its carry: (2,B) floats = g_{t0+T} and value row t0+T on
+// entry, g_{t0} and value row t0 on exit (chunks are processed from the LAST one to the first).
+struct GaeChunk {
+    int64_t T_total;
+    int64_t t0;
+    float* carry;
+};
+
 static int gae_forward_impl(const float* value, int64_t ldv, const float* reward, int64_t ldr, float* adv,
-                            int64_t lda, int64_t T, int64_t B, double gamma, double lambda, cudaStream_t stream) {
+                            int64_t lda, int64_t T, int64_t B, double gamma, double lambda, cudaStream_t stream,
+                            const GaeChunk* chunk = nullptr) {
     HPC_REQUIRE(T >= 0 && B >= 0, "gae_forward: negative size T=%lld B=%lld", (long long)T, (long long)B);
     if (T == 0 || B == 0) return HPC_RLL_OK;
     HPC_REQUIRE(value && reward && adv, "gae_forward: null pointer");
     HPC_REQUIRE(ldv >= B && ldr >= B && lda >= B, "gae_forward: row pitch smaller than B");
     HPC_REQUIRE(T < (int64_t(1) << 31) - 64 && B < (int64_t(1) << 31) - 512, "gae_forward: T/B exceed 2^31");
     const float* dtab = nullptr;
-    int rc = get_dtab(T, lambda, stream, &dtab);
+    int rc = get_dtab(chunk ? chunk->T_total : T, lambda, stream, &dtab);
     if (rc) return rc;
+    float* carry = chunk ? chunk->carry : nullptr;
+    const float* v_next = chunk ? chunk->carry + B : value + T * ldv;
+    if (chunk) dtab += 2 * chunk->t0;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
     int S = 0, seg_len = 0;
-    if (split_geometry(T, B, &S, &seg_len)) {
+    if (!chunk && split_geometry(T, B, &S, &seg_len)) {
         SplitScratch* sc = nullptr;
         rc = split_scratch(static_cast<size_t>(S) * static_cast<size_t>(B), stream, &sc);
         if (rc) return rc;
@@ -738,34 +797,43 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
         return HPC_RLL_OK;
     }
     int cfg = pick_cfg(B);
-    const bool tma = tma_ok_2d(value, B, ldv) && tma_ok_2d(reward, B, ldr);
+    if (cfg == 20) cfg = 13;
+    // the d_t slice of a stage is a 16-byte-aligned bulk copy: a chunk must start on an even row
+    const bool tma = tma_ok_2d(value, B, ldv) && tma_ok_2d(reward, B, ldr) && aligned16(dtab);
     if (!tma) cfg = 99;
     if (cfg >= 30 && cfg < 99 && !tma_ok_2d(adv, B, lda)) cfg = 7;  // output not TMA-describable: per-thread stores
+#define HPC_FWD(BT_, TT_, ST_) \
+    return launch_fwd_tma<BT_, TT_, ST_>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream, nullptr, nullptr, \
+                                         v_next, carry)
+#define HPC_FWD_ST(BT_, TT_, ST_) \
+    return launch_fwd_tma_st<BT_, TT_, ST_>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream, v_next, carry)
     switch (cfg) {
-        case 0: return launch_fwd_tma<64, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 1: return launch_fwd_tma<128, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 2: return launch_fwd_tma<32, 32, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 3: return launch_fwd_tma<64, 32, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 4: return launch_fwd_tma<128, 8, 4>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 5: return launch_fwd_tma<64, 8, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 6: return launch_fwd_tma<128, 32, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 7: return launch_fwd_tma<256, 8, 4>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 8: return launch_fwd_tma<256, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 10: return launch_fwd_tma<256, 4, 8>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 11: return launch_fwd_tma<256, 8, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 13: return launch_fwd_tma<32, 64, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        case 14: return launch_fwd_tma<32, 16, 12>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream);
-        // 30..: TMA-staged output (needs a TMA-describable adv as well)
-        case 30: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<256, 8, 4>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
-        case 31: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<128, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
-        case 32: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<256, 16, 3>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
-        case 33: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<256, 4, 6>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
-        case 34: if (tma_ok_2d(adv, B, lda)) return launch_fwd_tma_st<256, 4, 5>(value, ldv, reward, ldr, dtab, adv, lda, T, B, g, f, stream); break;
+        case 0: HPC_FWD(64, 16, 3);
+        case 1: HPC_FWD(128, 16, 3);
+        case 2: HPC_FWD(32, 32, 3);
+        case 3: HPC_FWD(64, 32, 3);
+        case 4: HPC_FWD(128, 8, 4);
+        case 5: HPC_FWD(64, 8, 6);
+        case 6: HPC_FWD(128, 32, 3);
+        case 7: HPC_FWD(256, 8, 4);
+        case 8: HPC_FWD(256, 16, 3);
+        case 10: HPC_FWD(256, 4, 8);
+        case 11: HPC_FWD(256, 8, 6);
+        case 13: HPC_FWD(32, 64, 6);
+        case 14: HPC_FWD(32, 16, 12);
+        // 30..: TMA-staged output (needs a TMA-describable adv as well; checked above)
+        case 30: HPC_FWD_ST(256, 8, 4);
+        case 31: HPC_FWD_ST(128, 16, 3);
+        case 32: HPC_FWD_ST(256, 16, 3);
+        case 33: HPC_FWD_ST(256, 4, 6);
+        case 34: HPC_FWD_ST(256, 4, 5);
         default: break;
     }
+#undef HPC_FWD
+#undef HPC_FWD_ST
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);
     gae_fwd_generic<false><<<grid, 128, 0, stream>>>(value, ldv, reward, ldr, dtab, adv, lda, static_cast<int>(T),
-                                                     static_cast<int>(B), g, f, nullptr);
+                                                     static_cast<int>(B), g, f, nullptr, v_next, carry);
     count_launch();
     HPC_LAUNCH_CHECK();
     return HPC_RLL_OK;
@@ -829,7 +897,7 @@ static int gae_forward_moments_impl(const float* value, const float* reward, flo
             const unsigned grid = static_cast<unsigned>((B + 127) / 128);
             nblocks = static_cast<int>(grid);
             gae_fwd_generic<true><<<grid, 128, 0, stream>>>(value, B, reward, B, dtab, adv, B, static_cast<int>(T),
-                                                            static_cast<int>(B), g, f, partials);
+                                                            static_cast<int>(B), g, f, partials, value + T * B, nullptr);
             count_launch();
             HPC_LAUNCH_CHECK();
         }
@@ -841,24 +909,30 @@ static int gae_forward_moments_impl(const float* value, const float* reward, flo
     return HPC_RLL_OK;
 }
 
+// Backward scan over `T` consecutive rows; chunk as above with carry = (ghat, dd of the previous row), chunks processed
+// from the FIRST one to the last.  Row T_total of grad_value is written by the launch that ends at the last row.
 static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int64_t ldgv, float* gr, int64_t ldgr,
-                             int64_t T, int64_t B, double gamma, double lambda, cudaStream_t stream) {
+                             int64_t T, int64_t B, double gamma, double lambda, cudaStream_t stream,
+                             const GaeChunk* chunk = nullptr) {
     HPC_REQUIRE(T >= 0 && B >= 0, "gae_backward: negative size T=%lld B=%lld", (long long)T, (long long)B);
     if (B == 0) return HPC_RLL_OK;
     HPC_REQUIRE(gv != nullptr, "gae_backward: null grad_value");
     if (T == 0) {  // value is (1,B): no advantage depends on it
-        HPC_CUDA(cudaMemsetAsync(gv, 0, sizeof(float) * static_cast<size_t>(B), stream));
+        if (!chunk) HPC_CUDA(cudaMemsetAsync(gv, 0, sizeof(float) * static_cast<size_t>(B), stream));
         return HPC_RLL_OK;
     }
     HPC_REQUIRE(grad_adv && gr, "gae_backward: null pointer");
     HPC_REQUIRE(ldg >= B && ldgv >= B && ldgr >= B, "gae_backward: row pitch smaller than B");
     HPC_REQUIRE(T < (int64_t(1) << 31) - 64 && B < (int64_t(1) << 31) - 512, "gae_backward: T/B exceed 2^31");
     const float* dtab = nullptr;
-    int rc = get_dtab(T, lambda, stream, &dtab);
+    int rc = get_dtab(chunk ? chunk->T_total : T, lambda, stream, &dtab);
     if (rc) return rc;
+    float* carry = chunk ? chunk->carry : nullptr;
+    const int write_last = (!chunk || chunk->t0 + T == chunk->T_total) ? 1 : 0;
+    if (chunk) dtab += 2 * chunk->t0;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
     int S = 0, seg_len = 0;
-    if (split_geometry(T, B, &S, &seg_len)) {
+    if (!chunk && split_geometry(T, B, &S, &seg_len)) {
         SplitScratch* sc = nullptr;
         rc = split_scratch(static_cast<size_t>(S) * static_cast<size_t>(B), stream, &sc);
         if (rc) return rc;
@@ -873,51 +947,135 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
         return HPC_RLL_OK;
     }
     int cfg = pick_cfg(B, true);
-    if (!tma_ok_2d(grad_adv, B, ldg)) cfg = 99;
+    if (cfg == 20) cfg = 13;
+    if (!(tma_ok_2d(grad_adv, B, ldg) && aligned16(dtab))) cfg = 99;
     if (cfg >= 30 && cfg < 99 && !(tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr))) cfg = 7;
+#define HPC_BWD(BT_, TT_, ST_) \
+    return launch_bwd_tma<BT_, TT_, ST_>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream, carry, write_last)
+#define HPC_BWD_ST(BT_, TT_, ST_) \
+    return launch_bwd_tma_st<BT_, TT_, ST_>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream, carry, write_last)
     switch (cfg) {
-        case 0: return launch_bwd_tma<64, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 1: return launch_bwd_tma<128, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 2: return launch_bwd_tma<32, 32, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 3: return launch_bwd_tma<64, 32, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 4: return launch_bwd_tma<128, 8, 4>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 5: return launch_bwd_tma<64, 8, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 6: return launch_bwd_tma<128, 32, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 7: return launch_bwd_tma<256, 8, 4>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 8: return launch_bwd_tma<256, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 10: return launch_bwd_tma<256, 4, 8>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 11: return launch_bwd_tma<256, 8, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 13: return launch_bwd_tma<32, 64, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        case 14: return launch_bwd_tma<32, 16, 12>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream);
-        // 30..: TMA-staged output (needs TMA-describable grad_value / grad_reward as well)
-        case 30: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<256, 8, 4>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
-        case 31: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<128, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
-        case 32: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<256, 16, 3>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
-        case 33: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<256, 4, 6>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
-        case 34: if (tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr)) return launch_bwd_tma_st<256, 4, 5>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, T, B, g, f, stream); break;
+        case 0: HPC_BWD(64, 16, 3);
+        case 1: HPC_BWD(128, 16, 3);
+        case 2: HPC_BWD(32, 32, 3);
+        case 3: HPC_BWD(64, 32, 3);
+        case 4: HPC_BWD(128, 8, 4);
+        case 5: HPC_BWD(64, 8, 6);
+        case 6: HPC_BWD(128, 32, 3);
+        case 7: HPC_BWD(256, 8, 4);
+        case 8: HPC_BWD(256, 16, 3);
+        case 10: HPC_BWD(256, 4, 8);
+        case 11: HPC_BWD(256, 8, 6);
+        case 13: HPC_BWD(32, 64, 6);
+        case 14: HPC_BWD(32, 16, 12);
+        // 30..: TMA-staged output (needs TMA-describable grad_value / grad_reward as well; checked above)
+        case 30: HPC_BWD_ST(256, 8, 4);
+        case 31: HPC_BWD_ST(128, 16, 3);
+        case 32: HPC_BWD_ST(256, 16, 3);
+        case 33: HPC_BWD_ST(256, 4, 6);
+        case 34: HPC_BWD_ST(256, 4, 5);
         default: break;
     }
+#undef HPC_BWD
+#undef HPC_BWD_ST
     const unsigned grid = static_cast<unsigned>((B + 127) / 128);
     gae_bwd_generic<<<grid, 128, 0, stream>>>(grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, static_cast<int>(T),
-                                              static_cast<int>(B), g, f);
+                                              static_cast<int>(B), g, f, carry, write_last);
     count_launch();
     HPC_LAUNCH_CHECK();
     return HPC_RLL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
-// host-buffer end-to-end path: column blocks pipelined over H2D / kernels / D2H
+// host-buffer end-to-end path: T-CHUNKED carry pipeline (round 2; replaces the column-block pipeline)
+//
+// The scan state between two row ranges is two floats per column, so a (T,B) problem whose operands live in host
+// memory is streamed as contiguous ROW RANGES: every copy is one 1-D DMA of rows*B*4 bytes (full 256 KB rows at
+// B=65536) in both directions, and every kernel launch is full width (the TMA-store kernels of the resident
+// path).  Forward walks the chunks from the last to the first (carry g, v), backward from the first to the
+// last (carry ghat, dd); stage i handles forward chunk nC-1-i and backward chunk i, so the host->device engine
+// streams value/reward/grad_adv rows while the device->host engine drains adv/grad_value/grad_reward rows of
+// earlier stages.  Three streams (H2D, compute, D2H) + per-slot events; kSlots stages in flight.
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct HostPipe {
     static constexpr int kSlots = 4;
     int dev = -1;
-    cudaStream_t stream[kSlots] = {};
-    float* buf[kSlots] = {};
-    size_t cap = 0;  // floats per slot
-    std::mutex mu;
+    bool busy = false;
+    cudaStream_t s_h2d = nullptr, s_k = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h[kSlots] = {}, ev_k[kSlots] = {}, ev_d[kSlots] = {};
+    cudaEvent_t done = nullptr;
+    float* buf = nullptr;
+    size_t cap = 0;  // floats
 };
-HostPipe g_hp;
+std::mutex g_hp_mu;
+std::vector<HostPipe*> g_hp_pool;
+
+// every concurrent host-entry caller gets its own pipe (streams, events, staging memory); pipes are pooled per device
+struct HostPipeLease {
+    HostPipe* p = nullptr;
+    ~HostPipeLease() {
+        if (p) {
+            std::lock_guard<std::mutex> lk(g_hp_mu);
+            p->busy = false;
+        }
+    }
+};
+
+int host_pipe_acquire(int dev, size_t floats, HostPipeLease* lease) {
+    HostPipe* hp = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_hp_mu);
+        for (HostPipe* c : g_hp_pool)
+            if (!c->busy && c->dev == dev) {
+                hp = c;
+                break;
+            }
+        if (!hp) {
+            hp = new HostPipe();
+            hp->dev = dev;
+            g_hp_pool.push_back(hp);
+        }
+        hp->busy = true;
+    }
+    lease->p = hp;
+    if (!hp->s_h2d) {
+        HPC_CUDA(cudaStreamCreateWithFlags(&hp->s_h2d, cudaStreamNonBlocking));
+        HPC_CUDA(cudaStreamCreateWithFlags(&hp->s_k, cudaStreamNonBlocking));
+        HPC_CUDA(cudaStreamCreateWithFlags(&hp->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < HostPipe::kSlots; ++i) {
+            HPC_CUDA(cudaEventCreateWithFlags(&hp->ev_h[i], cudaEventDisableTiming));
+            HPC_CUDA(cudaEventCreateWithFlags(&hp->ev_k[i], cudaEventDisableTiming));
+            HPC_CUDA(cudaEventCreateWithFlags(&hp->ev_d[i], cudaEventDisableTiming));
+        }
+        // the final wait sleeps instead of spinning: with one rank per GPU the host cores are shared
+        HPC_CUDA(cudaEventCreateWithFlags(&hp->done, cudaEventDisableTiming | cudaEventBlockingSync));
+    }
+    if (hp->cap < floats) {
+        if (hp->buf) {
+            HPC_CUDA(cudaStreamSynchronize(hp->s_d2h));
+            cudaFree(hp->buf);
+            hp->buf = nullptr;
+            hp->cap = 0;
+        }
+        HPC_CUDA(cudaMalloc(&hp->buf, floats * sizeof(float)));
+        hp->cap = floats;
+    }
+    return HPC_RLL_OK;
+}
+
+int64_t host_chunk_rows(int64_t T, int64_t B) {
+    static const long long forced = [] {
+        const char* e = getenv("HPC_RLL_HOST_CHUNK_ROWS");
+        return e ? atoll(e) : 0LL;
+    }();
+    int64_t R = forced >= 4 ? forced : (int64_t(1) << 20) / (B > 0 ? B : 1);  // ~4 MB per tensor per stage
+    R = (R / 4) * 4;  // whole 4-row TMA boxes; keeps every chunk's d_t slice 16-byte aligned
+    if (R < 4) R = 4;
+    const int64_t Tpad = ((T + 3) / 4) * 4;
+    if (R > Tpad) R = Tpad;
+    return R;
+}
 }  // namespace
 
 static int gae_host_impl(const float* h_value, const float* h_reward, const float* h_gadv, float* h_adv,
@@ -926,72 +1084,68 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
     HPC_REQUIRE(h_value && h_reward && h_adv, "gae_fwd_bwd_host: null forward buffer");
     const bool bwd = h_gadv != nullptr;
     HPC_REQUIRE(!bwd || (h_gvalue && h_greward), "gae_fwd_bwd_host: backward needs grad_value and grad_reward");
-    std::lock_guard<std::mutex> lk(g_hp.mu);
     int dev = 0;
     HPC_CUDA(cudaGetDevice(&dev));
-    // column block: multiple of 128 columns, ~8 MB per tensor per slot (32 blocks at T=1024, B=65536:
-    // pipeline fill/drain is ~1/32 of the copy time)
-    int64_t cb = (int64_t(2) << 20) / (T + 1);
-    cb = (cb / 128) * 128;
-    if (cb < 128) cb = 128;
-    // tuning knob (columns per block, multiple of 4): wider blocks = longer DMA rows, fewer pipeline stages
-    static const long long forced_cb = [] {
-        const char* e = getenv("HPC_RLL_HOST_BLOCK_COLS");
-        return e ? atoll(e) : 0LL;
-    }();
-    if (forced_cb >= 128) cb = (forced_cb / 4) * 4;
-    if (cb > B) cb = ((B + 3) / 4) * 4;
-    const size_t rows = static_cast<size_t>(T + 1);
-    const size_t per_tensor = rows * static_cast<size_t>(cb);
-    const size_t need = per_tensor * 6;
-    if (g_hp.dev != dev || g_hp.cap < need) {
-        for (int s = 0; s < HostPipe::kSlots; ++s) {
-            if (g_hp.buf[s]) cudaFree(g_hp.buf[s]);
-            g_hp.buf[s] = nullptr;
-            if (g_hp.dev != dev && g_hp.stream[s]) {
-                cudaStreamDestroy(g_hp.stream[s]);
-                g_hp.stream[s] = nullptr;
-            }
-        }
-        g_hp.cap = 0;
-        for (int s = 0; s < HostPipe::kSlots; ++s) {
-            if (!g_hp.stream[s]) HPC_CUDA(cudaStreamCreateWithFlags(&g_hp.stream[s], cudaStreamNonBlocking));
-            HPC_CUDA(cudaMalloc(&g_hp.buf[s], need * sizeof(float)));
-        }
-        g_hp.cap = need;
-        g_hp.dev = dev;
-    }
-    const size_t hp = static_cast<size_t>(B) * sizeof(float);  // host pitch
-    const size_t dp = static_cast<size_t>(cb) * sizeof(float); // device pitch
-    int slot = 0;
-    for (int64_t c0 = 0; c0 < B; c0 += cb, slot = (slot + 1) % HostPipe::kSlots) {
-        const int64_t w = (B - c0 < cb) ? (B - c0) : cb;
-        const size_t wb = static_cast<size_t>(w) * sizeof(float);
-        cudaStream_t st = g_hp.stream[slot];
-        float* d_value = g_hp.buf[slot];
-        float* d_reward = d_value + per_tensor;
-        float* d_adv = d_reward + per_tensor;
-        float* d_gadv = d_adv + per_tensor;
-        float* d_gvalue = d_gadv + per_tensor;
-        float* d_greward = d_gvalue + per_tensor;
-        // all host->device copies of the block first, then both kernels, then all device->host copies:
-        // the H2D and D2H copy engines then run back to back across the slots' streams
-        HPC_CUDA(cudaMemcpy2DAsync(d_value, dp, h_value + c0, hp, wb, rows, cudaMemcpyHostToDevice, st));
-        HPC_CUDA(cudaMemcpy2DAsync(d_reward, dp, h_reward + c0, hp, wb, rows - 1, cudaMemcpyHostToDevice, st));
-        if (bwd) HPC_CUDA(cudaMemcpy2DAsync(d_gadv, dp, h_gadv + c0, hp, wb, rows - 1, cudaMemcpyHostToDevice, st));
-        int rc = gae_forward_impl(d_value, cb, d_reward, cb, d_adv, cb, T, w, gamma, lambda, st);
+    const int64_t R = host_chunk_rows(T, B);
+    const int64_t nC = (T + R - 1) / R;
+    const size_t Bs = static_cast<size_t>(B);
+    const size_t chunk = static_cast<size_t>(R) * Bs;           // floats per staged tensor
+    const size_t slot = 6 * chunk + Bs;                          // + row T of grad_value in the last backward chunk
+    HostPipeLease lease;
+    int rc = host_pipe_acquire(dev, HostPipe::kSlots * slot + 4 * Bs, &lease);
+    if (rc) return rc;
+    HostPipe& hp = *lease.p;
+    float* carry_f = hp.buf + HostPipe::kSlots * slot;  // (2,B): g, value row
+    float* carry_b = carry_f + 2 * Bs;                  // (2,B): ghat, dd
+    // initial scan state: g = 0, v_next = value[T]; ghat = dd = 0
+    HPC_CUDA(cudaMemsetAsync(carry_f, 0, Bs * sizeof(float), hp.s_h2d));
+    HPC_CUDA(cudaMemcpyAsync(carry_f + Bs, h_value + static_cast<size_t>(T) * Bs, Bs * sizeof(float),
+                             cudaMemcpyHostToDevice, hp.s_h2d));
+    HPC_CUDA(cudaMemsetAsync(carry_b, 0, 2 * Bs * sizeof(float), hp.s_h2d));
+    for (int64_t i = 0; i < nC; ++i) {
+        const int s = static_cast<int>(i % HostPipe::kSlots);
+        float* d_value = hp.buf + s * slot;
+        float* d_reward = d_value + chunk;
+        float* d_adv = d_reward + chunk;
+        float* d_gadv = d_adv + chunk;
+        float* d_greward = d_gadv + chunk;
+        float* d_gvalue = d_greward + chunk;  // last: may hold one extra row
+        const int64_t kf = nC - 1 - i, kb = i;
+        const int64_t f0 = kf * R, frows = (T - f0 < R) ? (T - f0) : R;
+        const int64_t b0 = kb * R, brows = (T - b0 < R) ? (T - b0) : R;
+        const size_t fbytes = static_cast<size_t>(frows) * Bs * sizeof(float);
+        const size_t bbytes = static_cast<size_t>(brows) * Bs * sizeof(float);
+        // ---- host -> device (waits until the kernels of the stage that used this slot before have read it)
+        if (i >= HostPipe::kSlots) HPC_CUDA(cudaStreamWaitEvent(hp.s_h2d, hp.ev_k[s], 0));
+        HPC_CUDA(cudaMemcpyAsync(d_value, h_value + static_cast<size_t>(f0) * Bs, fbytes, cudaMemcpyHostToDevice, hp.s_h2d));
+        HPC_CUDA(cudaMemcpyAsync(d_reward, h_reward + static_cast<size_t>(f0) * Bs, fbytes, cudaMemcpyHostToDevice, hp.s_h2d));
+        if (bwd)
+            HPC_CUDA(cudaMemcpyAsync(d_gadv, h_gadv + static_cast<size_t>(b0) * Bs, bbytes, cudaMemcpyHostToDevice, hp.s_h2d));
+        HPC_CUDA(cudaEventRecord(hp.ev_h[s], hp.s_h2d));
+        // ---- kernels (wait for the inputs, and for the D2H copies that drained this slot's outputs)
+        HPC_CUDA(cudaStreamWaitEvent(hp.s_k, hp.ev_h[s], 0));
+        if (i >= HostPipe::kSlots) HPC_CUDA(cudaStreamWaitEvent(hp.s_k, hp.ev_d[s], 0));
+        GaeChunk cf{T, f0, carry_f};
+        rc = gae_forward_impl(d_value, B, d_reward, B, d_adv, B, frows, B, gamma, lambda, hp.s_k, &cf);
         if (rc) return rc;
         if (bwd) {
-            rc = gae_backward_impl(d_gadv, cb, d_gvalue, cb, d_greward, cb, T, w, gamma, lambda, st);
+            GaeChunk cb{T, b0, carry_b};
+            rc = gae_backward_impl(d_gadv, B, d_gvalue, B, d_greward, B, brows, B, gamma, lambda, hp.s_k, &cb);
             if (rc) return rc;
         }
-        HPC_CUDA(cudaMemcpy2DAsync(h_adv + c0, hp, d_adv, dp, wb, rows - 1, cudaMemcpyDeviceToHost, st));
+        HPC_CUDA(cudaEventRecord(hp.ev_k[s], hp.s_k));
+        // ---- device -> host
+        HPC_CUDA(cudaStreamWaitEvent(hp.s_d2h, hp.ev_k[s], 0));
+        HPC_CUDA(cudaMemcpyAsync(h_adv + static_cast<size_t>(f0) * Bs, d_adv, fbytes, cudaMemcpyDeviceToHost, hp.s_d2h));
         if (bwd) {
-            HPC_CUDA(cudaMemcpy2DAsync(h_gvalue + c0, hp, d_gvalue, dp, wb, rows, cudaMemcpyDeviceToHost, st));
-            HPC_CUDA(cudaMemcpy2DAsync(h_greward + c0, hp, d_greward, dp, wb, rows - 1, cudaMemcpyDeviceToHost, st));
+            const size_t gvbytes = bbytes + (b0 + brows == T ? Bs * sizeof(float) : 0);  // + row T at the end
+            HPC_CUDA(cudaMemcpyAsync(h_gvalue + static_cast<size_t>(b0) * Bs, d_gvalue, gvbytes, cudaMemcpyDeviceToHost, hp.s_d2h));
+            HPC_CUDA(cudaMemcpyAsync(h_greward + static_cast<size_t>(b0) * Bs, d_greward, bbytes, cudaMemcpyDeviceToHost, hp.s_d2h));
         }
+        HPC_CUDA(cudaEventRecord(hp.ev_d[s], hp.s_d2h));
     }
-    for (int s = 0; s < HostPipe::kSlots; ++s) HPC_CUDA(cudaStreamSynchronize(g_hp.stream[s]));
+    HPC_CUDA(cudaEventRecord(hp.done, hp.s_d2h));
+    HPC_CUDA(cudaEventSynchronize(hp.done));
     return HPC_RLL_OK;
 }
 
@@ -1044,6 +1198,27 @@ int hpc_rll_gae_backward_ld(const float* grad_adv, int64_t ld_grad_adv, float* g
                             double lambda, void* stream) {
     return hpcrll::gae_backward_impl(grad_adv, ld_grad_adv, grad_value, ld_grad_value, grad_reward, ld_grad_reward,
                                      T, B, gamma, lambda, hpcrll::as_stream(stream));
+}
+
+int hpc_rll_gae_forward_chunk(const float* value, const float* reward, float* adv, float* carry, int64_t T_total,
+                              int64_t t0, int64_t rows, int64_t B, double gamma, double lambda, void* stream) {
+    using namespace hpcrll;
+    HPC_REQUIRE(carry != nullptr, "gae_forward_chunk: null carry");
+    HPC_REQUIRE(t0 >= 0 && rows >= 0 && t0 + rows <= T_total, "gae_forward_chunk: rows [%lld, %lld) outside T=%lld",
+                (long long)t0, (long long)(t0 + rows), (long long)T_total);
+    GaeChunk c{T_total, t0, carry};
+    return gae_forward_impl(value, B, reward, B, adv, B, rows, B, gamma, lambda, as_stream(stream), &c);
+}
+
+int hpc_rll_gae_backward_chunk(const float* grad_adv, float* grad_value, float* grad_reward, float* carry,
+                               int64_t T_total, int64_t t0, int64_t rows, int64_t B, double gamma, double lambda,
+                               void* stream) {
+    using namespace hpcrll;
+    HPC_REQUIRE(carry != nullptr, "gae_backward_chunk: null carry");
+    HPC_REQUIRE(t0 >= 0 && rows >= 0 && t0 + rows <= T_total, "gae_backward_chunk: rows [%lld, %lld) outside T=%lld",
+                (long long)t0, (long long)(t0 + rows), (long long)T_total);
+    GaeChunk c{T_total, t0, carry};
+    return gae_backward_impl(grad_adv, B, grad_value, B, grad_reward, B, rows, B, gamma, lambda, as_stream(stream), &c);
 }
 
 int hpc_rll_gae_fwd_bwd_host(const float* h_value, const float* h_reward, const float* h_grad_adv, float* h_adv,

@@ -91,13 +91,44 @@ int hpc_rll_gae_forward_moments(const float* value, const float* reward, float* 
  * count <= 0: the element count is read from moments[2] (a caller-filled third double, so that sums and
  * count travel through one all-reduce and no host round trip is needed). */
 int hpc_rll_adv_stats(const double* moments, int64_t count, float* stats, void* stream);
-/* HOST-buffer entry (end-to-end path): pinned or pageable host arrays in, host arrays out.  Runs
- * forward and backward on the current device, pipelining column blocks over H2D copy / kernels /
- * D2H copy on internal streams; returns after all results have landed in the host buffers.
- * Any of h_grad_adv/h_grad_value/h_grad_reward may be NULL together (forward only). */
+/* T-CHUNKED scan (round 2): rows [t0, t0+rows) of a T_total-row problem, the scan state carried in `carry`
+ * (2,B) fp32 on the device.  Bit-identical to the monolithic call (the per-column recurrence is sequential; chunking
+ * does not re-associate it).  This is what lets a (T,B) problem be streamed through the device as contiguous row
+ * ranges (hpc_rll_gae_fwd_bwd_host) or produced/consumed chunk by chunk by a rollout collector.
+ *   forward : chunks are processed from the LAST one to the first.  carry[0:B] = g (0 before the first call),
+ *             carry[B:2B] = the value row that follows the chunk (value[T_total] before the first call); on return
+ *             g at row t0 and value row t0.  value/reward/adv are (rows,B) (no extra value row).
+ *   backward: chunks are processed from the FIRST one to the last.  carry = (ghat, dd of the previous row), zeros
+ *             before the first call.  grad_value is (rows,B), plus row `rows` (= global row T_total) in the call
+ *             with t0 + rows == T_total.
+ * t0 must be even for the TMA path (else a generic CUDA kernel runs). */
+int hpc_rll_gae_forward_chunk(const float* value, const float* reward, float* adv, float* carry, int64_t T_total,
+                              int64_t t0, int64_t rows, int64_t B, double gamma, double lambda, void* stream);
+int hpc_rll_gae_backward_chunk(const float* grad_adv, float* grad_value, float* grad_reward, float* carry,
+                               int64_t T_total, int64_t t0, int64_t rows, int64_t B, double gamma, double lambda,
+                               void* stream);
+/* HOST-buffer entry (end-to-end path): pinned (or pageable) host arrays in, host arrays out.  Runs forward and
+ * backward on the current device as a T-chunked carry pipeline: contiguous row ranges stream over the H2D engine,
+ * full-width kernels, the D2H engine drains results, all overlapped on internal streams (a pool of pipes: concurrent
+ * callers do not serialise); returns after all results have landed in the host buffers (sleeping, not spinning).
+ * Any of h_grad_adv/h_grad_value/h_grad_reward may be NULL together (forward only).
+ * Tuning: HPC_RLL_HOST_CHUNK_ROWS (rows per stage, multiple of 4; default ~4 MB per tensor per stage). */
 int hpc_rll_gae_fwd_bwd_host(const float* h_value, const float* h_reward, const float* h_grad_adv, float* h_adv,
                              float* h_grad_value, float* h_grad_reward, int64_t T, int64_t B, double gamma,
                              double lambda);
+
+/* ---- host placement (NUMA) --------------------------------------------------------------------
+ * A B200 box has its GPUs split over two CPU sockets; host buffers that feed a GPU over PCIe should live on that
+ * GPU's socket, or eight ranks push all their DMA traffic through one socket's DRAM and the inter-socket link.
+ *   hpc_rll_device_numa_node     NUMA node of CUDA device `device` (sysfs numa_node of its PCI function), -1 unknown
+ *   hpc_rll_bind_thread_to_device  restrict the CALLING thread to that node's CPUs (threads it spawns inherit it)
+ *                                and prefer that node for its page allocations; returns the node or -1 (left as is)
+ *   hpc_rll_host_alloc / _free   page-locked host memory whose pages were first touched on that node
+ *                                (mmap + best-effort mbind + touch by node-pinned threads + cudaHostRegister) */
+int hpc_rll_device_numa_node(int device);
+int hpc_rll_bind_thread_to_device(int device);
+void* hpc_rll_host_alloc(size_t bytes, int device);
+int hpc_rll_host_free(void* ptr);
 
 /* ---- TD(lambda) ----------------------------------------------------------------------------
  * replaces TdLambdaForward / TdLambdaBackward (/root/reference/src/rl_utils/td_lambda.cu:8-52, kernels

@@ -142,26 +142,97 @@ def test_gae_full_size_properties():
         assert np.array_equal(host(r.grad[:, sl]), ob["reward"])
 
 
-def test_gae_host_entry_matches_device_path():
-    """hpc_rll_gae_fwd_bwd_host (pinned host buffers, chunked H2D/compute/D2H pipeline)."""
+@pytest.mark.parametrize("T,B,rows", [(1024, 4096, 32), (203, 1300, 16), (203, 1300, 60), (37, 516, 4), (37, 516, 5), (64, 1301, 8),
+                                      (50, 40000, 12), (9, 70000, 4)])
+def test_gae_chunked_scan_is_bit_identical(T, B, rows):
+    """hpc_rll_gae_forward_chunk / _backward_chunk: the scan cut into row ranges with the state carried in a (2,B)
+    buffer gives the same BITS as the monolithic call and the oracle (incl. a ragged last chunk, B % 4 != 0 ->
+    generic kernel, wide B -> TMA-store kernels)."""
     need_cuda()
     from di_hpc_b200 import _abi
-    g = rng(11)
-    T, B = 257, 9000
-    value = torch.from_numpy(g.standard_normal((T + 1, B), dtype=np.float32)).pin_memory()
-    reward = torch.from_numpy(g.standard_normal((T, B), dtype=np.float32)).pin_memory()
-    gadv = torch.from_numpy(g.standard_normal((T, B), dtype=np.float32)).pin_memory()
-    adv = torch.empty((T, B)).pin_memory()
-    gv = torch.empty((T + 1, B)).pin_memory()
-    gr = torch.empty((T, B)).pin_memory()
-    _abi.check(_abi.lib().hpc_rll_gae_fwd_bwd_host(value.data_ptr(), reward.data_ptr(), gadv.data_ptr(),
-                                                   adv.data_ptr(), gv.data_ptr(), gr.data_ptr(), T, B, 0.99, 0.97),
-               "gae_fwd_bwd_host")
-    # the last (narrow) column block may take the T-split path: tolerance instead of bit equality
-    ob = orc.gae_backward(gadv.numpy())
-    same(adv.numpy(), orc.gae_forward(value.numpy(), reward.numpy()), False)
-    same(gv.numpy(), ob["value"], False)
-    same(gr.numpy(), ob["reward"], False)
+    g = rng(T * 7 + B + rows)
+    value = g.standard_normal((T + 1, B), dtype=np.float32)
+    reward = g.standard_normal((T, B), dtype=np.float32)
+    gadv = g.standard_normal((T, B), dtype=np.float32)
+    v, r, ga = dev(value), dev(reward), dev(gadv)
+    adv, gv, gr = torch.full((T, B), 7.0, device="cuda"), torch.full((T + 1, B), 7.0, device="cuda"), \
+        torch.full((T, B), 7.0, device="cuda")
+    L = _abi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    nC = (T + rows - 1) // rows
+    cf = torch.zeros(2, B, device="cuda")
+    cf[1] = v[T]
+    for k in reversed(range(nC)):
+        t0, n = k * rows, min(rows, T - k * rows)
+        _abi.check(L.hpc_rll_gae_forward_chunk(v[t0].data_ptr(), r[t0].data_ptr(), adv[t0].data_ptr(), cf.data_ptr(),
+                                               T, t0, n, B, 0.95, 0.9, st), "fwd_chunk")
+    cb = torch.zeros(2, B, device="cuda")
+    for k in range(nC):
+        t0, n = k * rows, min(rows, T - k * rows)
+        _abi.check(L.hpc_rll_gae_backward_chunk(ga[t0].data_ptr(), gv[t0].data_ptr(), gr[t0].data_ptr(),
+                                                cb.data_ptr(), T, t0, n, B, 0.95, 0.9, st), "bwd_chunk")
+    torch.cuda.synchronize()
+    ob = orc.gae_backward(gadv, 0.95, 0.9)
+    assert np.array_equal(host(adv), orc.gae_forward(value, reward, 0.95, 0.9))
+    assert np.array_equal(host(gv), ob["value"])
+    assert np.array_equal(host(gr), ob["reward"])
+    rc = L.hpc_rll_gae_forward_chunk(v.data_ptr(), r.data_ptr(), adv.data_ptr(), cf.data_ptr(), T, T - 1, 4, B, 0.95,
+                                     0.9, st)
+    assert rc == 1 and b"outside" in L.hpc_rll_last_error()
+
+
+@pytest.mark.parametrize("T,B,numa", [(257, 9000, False), (1024, 65536, True), (100, 1301, False), (5, 64, True)])
+def test_gae_host_entry_matches_oracle(T, B, numa):
+    """di_hpc_b200.host.gae_fwd_bwd_host -> hpc_rll_gae_fwd_bwd_host: host buffers in, host buffers out through the
+    T-chunked H2D / kernel / D2H pipeline; bit-exact vs the oracle (chunking does not re-associate the scan).
+    numa=True uses the library's NUMA-local page-locked allocator, otherwise torch's pin_memory."""
+    need_cuda()
+    from di_hpc_b200 import host as hp
+    g = rng(11 + T + B)
+    if numa:
+        value, reward, gadv = hp.pinned_empty((T + 1, B)), hp.pinned_empty((T, B)), hp.pinned_empty((T, B))
+        out = (hp.pinned_empty((T, B)), hp.pinned_empty((T + 1, B)), hp.pinned_empty((T, B)))
+        value.copy_(torch.from_numpy(g.standard_normal((T + 1, B), dtype=np.float32)))
+        reward.copy_(torch.from_numpy(g.standard_normal((T, B), dtype=np.float32)))
+        gadv.copy_(torch.from_numpy(g.standard_normal((T, B), dtype=np.float32)))
+    else:
+        value = torch.from_numpy(g.standard_normal((T + 1, B), dtype=np.float32)).pin_memory()
+        reward = torch.from_numpy(g.standard_normal((T, B), dtype=np.float32)).pin_memory()
+        gadv = torch.from_numpy(g.standard_normal((T, B), dtype=np.float32)).pin_memory()
+        out = None
+    for _ in range(2):  # second call reuses the pooled pipe
+        adv, gv, gr = hp.gae_fwd_bwd_host(value, reward, gadv, 0.99, 0.97, out=out)
+    if T * B <= 1 << 22:
+        ob = orc.gae_backward(gadv.numpy())
+        assert np.array_equal(adv.numpy(), orc.gae_forward(value.numpy(), reward.numpy()))
+        assert np.array_equal(gv.numpy(), ob["value"])
+        assert np.array_equal(gr.numpy(), ob["reward"])
+    else:  # full C1 size: column slabs through the oracle + the device-resident path for everything
+        from di_hpc_b200.rl_utils.gae import GAE
+        for sl in (slice(0, 130), slice(B - 70, B)):
+            assert np.array_equal(adv[:, sl].numpy(), orc.gae_forward(value[:, sl].numpy().copy(),
+                                                                      reward[:, sl].numpy().copy()))
+            ob = orc.gae_backward(gadv[:, sl].numpy().copy())
+            assert np.array_equal(gv[:, sl].numpy(), ob["value"]) and np.array_equal(gr[:, sl].numpy(), ob["reward"])
+        v = value.cuda().requires_grad_(True)
+        r = reward.cuda().requires_grad_(True)
+        a = GAE(T, B)(v, r)
+        a.backward(gadv.cuda())
+        assert torch.equal(a.detach().cpu(), adv) and torch.equal(v.grad.cpu(), gv) and torch.equal(r.grad.cpu(), gr)
+    fwd_only = hp.gae_fwd_bwd_host(value, reward, None, 0.99, 0.97)
+    assert torch.equal(fwd_only, adv)
+
+
+def test_host_numa_helpers():
+    need_cuda()
+    from di_hpc_b200 import host as hp
+    node = hp.device_numa_node(0)
+    assert node >= -1
+    t = hp.pinned_empty((3, 1000))
+    assert t.shape == (3, 1000) and t.is_pinned() and float(t.abs().sum()) == 0.0
+    t.fill_(2.0)
+    assert float(t.cuda().sum().item()) == 6000.0
+    del t
 
 
 def test_gae_argument_errors():

@@ -47,8 +47,35 @@ def wide_and_fused():
         torch.autograd.grad(UPGO(T, B, N)(t, torch.rand(T, B, device=D), a, r(T, B), v.detach()), [t], grad_outputs=ONE)
 
 
+def chunked_and_host():
+    """round 2: T-chunked scan with a carried state (incl. the TMA-store kernels on a chunk) and the host-buffer
+    pipeline (three streams, per-slot events, pooled staging memory)"""
+    from di_hpc_b200 import host as hp
+    L = _abi.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    for T, B, rows in ((23, 40000, 8), (23, 516, 4), (10, 133, 4)):
+        v, rew, ga = r(T + 1, B), r(T, B), r(T, B)
+        adv, gv, gr = torch.empty(T, B, device=D), torch.empty(T + 1, B, device=D), torch.empty(T, B, device=D)
+        cf, cb = torch.zeros(2, B, device=D), torch.zeros(2, B, device=D)
+        cf[1] = v[T]
+        nC = (T + rows - 1) // rows
+        for k in reversed(range(nC)):
+            t0, n = k * rows, min(rows, T - k * rows)
+            _abi.check(L.hpc_rll_gae_forward_chunk(v[t0].data_ptr(), rew[t0].data_ptr(), adv[t0].data_ptr(),
+                                                   cf.data_ptr(), T, t0, n, B, 0.99, 0.97, st), "fwd_chunk")
+        for k in range(nC):
+            t0, n = k * rows, min(rows, T - k * rows)
+            _abi.check(L.hpc_rll_gae_backward_chunk(ga[t0].data_ptr(), gv[t0].data_ptr(), gr[t0].data_ptr(),
+                                                    cb.data_ptr(), T, t0, n, B, 0.99, 0.97, st), "bwd_chunk")
+    T, B = 40, 40000
+    hv, hr, hg = torch.randn(T + 1, B).pin_memory(), torch.randn(T, B).pin_memory(), torch.randn(T, B).pin_memory()
+    hp.gae_fwd_bwd_host(hv, hr, hg)
+    hp.gae_fwd_bwd_host(hv, hr, None)
+
+
 def main():
     wide_and_fused()
+    chunked_and_host()
     for T, B, N in ((37, 132, 6), (16, 260, 16), (9, 64, 40)):
         v, rew = r(T + 1, B).requires_grad_(True), r(T, B).requires_grad_(True)
         for cfg in (-1, 0, 2, 13, 20, 99):
