@@ -25,6 +25,7 @@ SIGNATURES = {
     "hpc_rll_launch_count": (ctypes.c_uint64, []),
     "hpc_rll_workspace_bytes": (c_sz, [c_int, c_i64, c_i64, c_i64]),
     "hpc_rll_debug_set_config": (c_int, [c_int, c_int]),
+    "hpc_rll_axpby": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "hpc_rll_gae_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
     "hpc_rll_gae_backward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
     "hpc_rll_gae_forward_moments": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl, c_vp, c_sz, c_vp]),

@@ -48,4 +48,34 @@ int launch_scale_copy(const float* in, const float* scale_dev, float* out, int64
     return HPC_RLL_OK;
 }
 
+// out = a[0]*x + b[0]*y (b / y may be null: out = a[0]*x); a, b are DEVICE scalars.  Used by the legacy
+// `hpc_rl_utils` shim, whose backward entry points only receive buffers that are linear in the upstream gradients.
+__global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ a, const float* __restrict__ x,
+                                                     const float* __restrict__ b, const float* __restrict__ y,
+                                                     float* __restrict__ out, int64_t n) {
+    const float sa = __ldg(a);
+    const float sb = (b != nullptr && y != nullptr) ? __ldg(b) : 0.f;
+    const int64_t nth = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += nth) {
+        float v = sa * ld_stream(x + i);
+        if (y != nullptr && b != nullptr) v = fmaf(sb, ld_stream(y + i), v);
+        st_stream(out + i, v);
+    }
+}
+
 }  // namespace hpcrll
+
+extern "C" int hpc_rll_axpby(const float* a, const float* x, const float* b, const float* y, float* out, int64_t n,
+                             void* stream) {
+    using namespace hpcrll;
+    HPC_REQUIRE(n >= 0, "axpby: negative n");
+    if (n == 0) return HPC_RLL_OK;
+    HPC_REQUIRE(a && x && out, "axpby: null pointer");
+    int64_t blocks = (n + 255) / 256;
+    const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+    if (blocks > cap) blocks = cap;
+    axpby_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(a, x, b, y, out, n);
+    count_launch();
+    HPC_LAUNCH_CHECK();
+    return HPC_RLL_OK;
+}

@@ -15,7 +15,7 @@
 #include <random>
 #include <vector>
 
-#include "hpc_rll_b200.h"
+#include "common.h"
 
 namespace {
 
@@ -221,6 +221,8 @@ py::list group_pad_nd(const std::vector<torch::Tensor>& inputs, int ndim, int gr
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+    hpcrl::register_fast_ops(m);  // C++ autograd functions behind hpc_rll.rl_utils (fast_ops.cpp)
+    hpcrl::register_legacy(m);    // the reference's 19 hot-path `hpc_rl_utils` names (legacy.cpp)
     m.def("pad_nd", &pad_nd, "pad a list of n-D tensors: (new_x, mask, flat shapes)");
     m.def("group_pad_nd", &group_pad_nd, "sort + split + pad in one call");
     m.def("unpad_nd", [](const torch::Tensor& x, const std::vector<int>& s, int ndim) { return unpad_forward(x, s, ndim); },

@@ -59,6 +59,12 @@ size_t hpc_rll_workspace_bytes(int op, int64_t T, int64_t B, int64_t N);
 /* tuning/debug: force kernel configuration `cfg` for `op` (-1 = automatic) */
 int hpc_rll_debug_set_config(int op, int cfg);
 
+/* out[i] = a[0]*x[i] + b[0]*y[i]  (a, b DEVICE scalars; b and y may be NULL together: out = a[0]*x).  Glue for
+ * the legacy `hpc_rl_utils` tensor-list shim (di_hpc_b200/csrc_torch/legacy.cpp), whose backward entry points
+ * (/root/reference/src/rl_utils/entry.cpp:24-38) receive only buffers that are linear in the upstream gradients. */
+int hpc_rll_axpby(const float* a, const float* x, const float* b, const float* y, float* out, int64_t n,
+                  void* stream);
+
 /* ---- GAE ------------------------------------------------------------------------------------
  * replaces GaeForward (/root/reference/src/rl_utils/gae.cu:8-28, kernel
  * include/hpc/rll/cuda/rl_utils/gae_kernel.h:10-29); semantics of hpc_rll/origin/gae.py:28-37.
