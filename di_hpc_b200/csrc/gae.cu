@@ -33,6 +33,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "reduce.cuh"
@@ -1064,17 +1065,52 @@ int host_pipe_acquire(int dev, size_t floats, HostPipeLease* lease) {
     return HPC_RLL_OK;
 }
 
-int64_t host_chunk_rows(int64_t T, int64_t B) {
-    static const long long forced = [] {
+// Stage heights of the T-chunked pipeline.  Measured on B200 / PCIe Gen5 (profiles/r02_e2e.md): every copy costs
+// ~10 us of DMA set-up on top of bytes/50 GB/s (duplex), i.e. ~30 us per stage and direction, while the first stage's
+// H2D copy and the last stage's D2H copy cannot overlap with anything (fill / drain).  Uniform 64-row stages (16 MB
+// copies) lose 2 x 0.87 ms to fill/drain; uniform 8-row stages lose 128 x 45 us to set-up.  So the heights RAMP:
+// R0, R0, 2 R0, 4 R0 ... Rmax, Rmax ... 4 R0, 2 R0, R0, R0 -- short stages where nothing overlaps, long ones in between.
+// The list is a palindrome: the backward walks it from row 0 up, the forward from row T down.
+// HPC_RLL_HOST_CHUNK_ROWS="r0:rmax" (or one number = uniform) overrides; rows are multiples of 4 (whole TMA boxes,
+// 16-byte aligned d_t slices); T % 4 extra rows ride in the stage that touches row T.
+std::vector<int64_t> host_schedule(int64_t T, int64_t B) {
+    static const std::pair<long long, long long> forced = [] {
         const char* e = getenv("HPC_RLL_HOST_CHUNK_ROWS");
-        return e ? atoll(e) : 0LL;
+        if (!e) return std::make_pair(0LL, 0LL);
+        const long long a = atoll(e);
+        const char* c = strchr(e, ':');
+        return std::make_pair(a, c ? atoll(c + 1) : a);
     }();
-    int64_t R = forced >= 4 ? forced : (int64_t(1) << 20) / (B > 0 ? B : 1);  // ~4 MB per tensor per stage
-    R = (R / 4) * 4;  // whole 4-row TMA boxes; keeps every chunk's d_t slice 16-byte aligned
-    if (R < 4) R = 4;
-    const int64_t Tpad = ((T + 3) / 4) * 4;
-    if (R > Tpad) R = Tpad;
-    return R;
+    const int64_t row_bytes = 4 * (B > 0 ? B : 1);
+    auto round4 = [](int64_t r) { return r < 4 ? int64_t(4) : (r / 4) * 4; };
+    int64_t r0 = round4(forced.first >= 4 ? forced.first : (int64_t(2) << 20) / row_bytes);
+    int64_t rmax = round4(forced.second >= 4 ? forced.second : (int64_t(32) << 20) / row_bytes);
+    if (rmax < r0) rmax = r0;
+    const int64_t T4 = (T / 4) * 4, rem = T - T4;
+    std::vector<int64_t> sizes;
+    if (T4 < 2 * r0) {
+        sizes.push_back(T);
+        return sizes;
+    }
+    std::vector<int64_t> up;  // r0, r0, 2 r0, 4 r0, ... while both ramps still fit
+    int64_t used = 0;
+    for (int64_t r = r0, k = 0; r <= rmax; ++k) {
+        if (2 * (used + r) > T4) break;
+        up.push_back(r);
+        used += r;
+        if (k >= 1) r *= 2;
+    }
+    int64_t middle = T4 - 2 * used;
+    const int64_t top = up.empty() ? r0 : up.back();
+    sizes = up;
+    while (middle >= 2 * top) {
+        sizes.push_back(top);
+        middle -= top;
+    }
+    if (middle > 0) sizes.push_back(middle);  // multiple of 4 by construction
+    for (size_t i = up.size(); i-- > 0;) sizes.push_back(up[i]);
+    sizes.back() += rem;  // the stage that ends at row T (backward order); the forward sees it first
+    return sizes;
 }
 }  // namespace
 
@@ -1086,8 +1122,15 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
     HPC_REQUIRE(!bwd || (h_gvalue && h_greward), "gae_fwd_bwd_host: backward needs grad_value and grad_reward");
     int dev = 0;
     HPC_CUDA(cudaGetDevice(&dev));
-    const int64_t R = host_chunk_rows(T, B);
-    const int64_t nC = (T + R - 1) / R;
+    // stage heights; backward stage i = rows [off[i], off[i+1]) ascending, forward stage i = the mirrored range
+    const std::vector<int64_t> sizes = host_schedule(T, B);
+    const int64_t nC = static_cast<int64_t>(sizes.size());
+    std::vector<int64_t> off(nC + 1, 0);
+    int64_t R = 0;
+    for (int64_t i = 0; i < nC; ++i) {
+        off[i + 1] = off[i] + sizes[i];
+        if (sizes[i] > R) R = sizes[i];
+    }
     const size_t Bs = static_cast<size_t>(B);
     const size_t chunk = static_cast<size_t>(R) * Bs;           // floats per staged tensor
     const size_t slot = 6 * chunk + Bs;                          // + row T of grad_value in the last backward chunk
@@ -1110,9 +1153,9 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
         float* d_gadv = d_adv + chunk;
         float* d_greward = d_gadv + chunk;
         float* d_gvalue = d_greward + chunk;  // last: may hold one extra row
-        const int64_t kf = nC - 1 - i, kb = i;
-        const int64_t f0 = kf * R, frows = (T - f0 < R) ? (T - f0) : R;
-        const int64_t b0 = kb * R, brows = (T - b0 < R) ? (T - b0) : R;
+        // the palindrome read from the other end: forward stage i covers the rows the backward covers in stage nC-1-i
+        const int64_t f0 = off[nC - 1 - i], frows = sizes[nC - 1 - i];
+        const int64_t b0 = off[i], brows = sizes[i];
         const size_t fbytes = static_cast<size_t>(frows) * Bs * sizeof(float);
         const size_t bbytes = static_cast<size_t>(brows) * Bs * sizeof(float);
         // ---- host -> device (waits until the kernels of the stage that used this slot before have read it)

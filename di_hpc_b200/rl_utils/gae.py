@@ -10,7 +10,7 @@ reference (gae.py:20-61).  Differences, all deliberate (DESIGN.md "Deviations"):
 """
 import torch
 
-from .. import _abi
+from .. import _abi, _ext
 
 
 class GAEFunction(torch.autograd.Function):
@@ -117,4 +117,7 @@ class GAE(torch.nn.Module):
         """
         assert (value.is_cuda)
         assert (reward.is_cuda)
+        fast = _ext.fast()
+        if fast is not None:  # C++ autograd function (csrc_torch/fast_ops.cpp); GAEFunction is its ctypes-bound twin
+            return fast.gae(value, reward, float(gamma), float(lambda_))
         return GAEFunction.apply(value, reward, gamma, lambda_)

@@ -23,27 +23,9 @@ _seed = itertools.count(0x5EED)
 _F32 = torch.float32
 
 
-def _load_ext():
-    """The thin torch/pybind layer (di_hpc_b200/csrc_torch/ext.cpp) does the per-tensor host work in C++.
-    It is optional: without it the same CUDA kernels are driven through ctypes from Python (slower host
-    side, identical results)."""
-    import glob
-    import importlib.util
-    import os
-    from .._abi import LIB_PATH
-    cands = glob.glob(os.path.join(os.path.dirname(LIB_PATH), "hpc_rl_utils_b200*.so"))
-    if not cands:
-        return None
-    try:
-        spec = importlib.util.spec_from_file_location("hpc_rl_utils_b200", cands[0])
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        return mod
-    except Exception:  # e.g. built against another torch: the ctypes path still works
-        return None
+from .. import _ext as _ext_loader
 
-
-_ext = _load_ext()
+_ext = _ext_loader.load()  # list handling in C++ (csrc_torch/ext.cpp); None -> same kernels through ctypes
 
 
 def cum(t) -> int:

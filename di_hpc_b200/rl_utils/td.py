@@ -18,7 +18,7 @@ from typing import Optional
 
 import torch
 
-from .. import _abi
+from .. import _abi, _ext
 
 
 def _nstep_common(q_like, action, next_n_action, reward, done, weight, B):
@@ -116,6 +116,9 @@ class TDLambda(torch.nn.Module):
         assert (reward.is_cuda)
         if weight is not None:
             assert (weight.is_cuda)
+        fast = _ext.fast()
+        if fast is not None:
+            return fast.td_lambda(value, reward, weight, float(gamma), float(lambda_), int(self.global_B))
         return TDLambdaFunction.apply(value, reward, weight, gamma, lambda_, self.global_B)
 
 
@@ -228,6 +231,10 @@ class QNStepTD(torch.nn.Module):
             assert (t.is_cuda)
         if weight is not None:
             assert (weight.is_cuda)
+        fast = _ext.fast()
+        if fast is not None:
+            return tuple(fast.q_nstep_td(q, next_n_q, action, next_n_action, reward, done, weight, float(gamma),
+                                         bool(self._fn.RESCALE), int(self.global_B)))
         return self._fn.apply(q, next_n_q, action, next_n_action, reward, done, weight, gamma, self.global_B)
 
 
@@ -331,6 +338,10 @@ class DistNStepTD(torch.nn.Module):
         if self.check_positive:
             batch_range = torch.arange(action.shape[0], device=action.device)
             assert (dist[batch_range, action] > 0.0).all(), ("dist act", dist[batch_range, action], "dist:", dist)
+        fast = _ext.fast()
+        if fast is not None:
+            return tuple(fast.dist_nstep_td(dist, next_n_dist, action, next_n_action, reward, done, weight,
+                                            float(gamma), float(v_min), float(v_max), int(self.global_B)))
         return DistNStepTDFunction.apply(dist, next_n_dist, action, next_n_action, reward, done, weight, gamma, v_min,
                                          v_max, self.global_B)
 
@@ -426,6 +437,10 @@ class QRDQNNStepTDError(torch.nn.Module):
             assert (weight.is_cuda)
         if value_gamma is not None:
             assert (value_gamma.is_cuda)
+        fast = _ext.fast()
+        if fast is not None:
+            return tuple(fast.qrdqn_nstep_td(q, next_n_q, action, next_n_action, reward, done, weight, value_gamma,
+                                             float(gamma), int(self.global_B)))
         return QRDQNNStepTDErrorFunction.apply(q, next_n_q, action, next_n_action, reward, done, weight, value_gamma,
                                                gamma, self.global_B)
 
@@ -529,5 +544,9 @@ class IQNNStepTDError(torch.nn.Module):
             assert (weight.is_cuda)
         if value_gamma is not None:
             assert (value_gamma.is_cuda)
+        fast = _ext.fast()
+        if fast is not None:
+            return tuple(fast.iqn_nstep_td(q, next_n_q, action, next_n_action, reward, done, replay_quantiles, weight,
+                                           value_gamma, float(gamma), float(kappa), int(self.global_B)))
         return IQNNStepTDErrorFunction.apply(q, next_n_q, action, next_n_action, reward, done, replay_quantiles,
                                              weight, value_gamma, gamma, kappa, self.global_B)

@@ -3,7 +3,7 @@ Same constructor ``UPGO(T, B, N)`` and ``forward(target_output, rhos, action, re
 bootstrap_values)`` (upgo.py:46-79); the loss is a shape-(1,) tensor."""
 import torch
 
-from .. import _abi
+from .. import _abi, _ext
 
 
 class UpgoFunction(torch.autograd.Function):
@@ -81,4 +81,7 @@ class UPGO(torch.nn.Module):
         assert (action.is_cuda)
         assert (rewards.is_cuda)
         assert (bootstrap_values.is_cuda)
+        fast = _ext.fast()
+        if fast is not None:
+            return fast.upgo(target_output, rhos, action, rewards, bootstrap_values, int(self.global_B))
         return UpgoFunction.apply(target_output, rhos, action, rewards, bootstrap_values, self.global_B)

@@ -5,7 +5,7 @@ from collections import namedtuple
 
 import torch
 
-from .. import _abi
+from .. import _abi, _ext
 
 hpc_vtrace_loss = namedtuple('hpc_vtrace_loss', ['policy_loss', 'value_loss', 'entropy_loss'])
 
@@ -105,6 +105,11 @@ class VTrace(torch.nn.Module):
         assert (reward.is_cuda)
         if weight is not None:
             assert (weight.is_cuda)
+        fast = _ext.fast()
+        if fast is not None:
+            return hpc_vtrace_loss(*fast.vtrace(target_output, behaviour_output, action, value, reward, weight,
+                                                float(gamma), float(lambda_), float(rho_clip_ratio),
+                                                float(c_clip_ratio), float(rho_pg_clip_ratio), int(self.global_B)))
         pg_loss, value_loss, entropy_loss = VtraceFunction.apply(target_output, behaviour_output, action, value,
                                                                  reward, weight, gamma, lambda_, rho_clip_ratio,
                                                                  c_clip_ratio, rho_pg_clip_ratio, self.global_B)
