@@ -550,6 +550,7 @@ def run_ours(args):
         ops = ops_block(torch, peak)
 
     if rank == 0:
+        hostapi.unbind()  # the CPU baseline gets every host core and both sockets' memory, like the reference arm
         base, _ = cpu_baseline(T, B, 5) if world == 1 else (None, None)
         line = {"metric": METRIC, "value": value_metric, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

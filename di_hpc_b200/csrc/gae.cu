@@ -37,6 +37,7 @@
 #include <vector>
 
 #include "reduce.cuh"
+#include "scan_lookback.cuh"
 #include "scan_pipe.cuh"
 
 namespace hpcrll {
@@ -451,134 +452,112 @@ __global__ void __launch_bounds__(128) gae_bwd_generic(const float* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// T-split kernels for the small-batch regime (few columns, long T: e.g. the reference's own test shape
-// T=1024, B=64, tests/test_gae.py:10-11).  With only B/32 warps of work the column scan is latency
-// bound, so T is cut into S segments that run in parallel (grid = column tiles x S):
-//   pass 1: every segment scans its rows from a zero carry and publishes its aggregate
-//           (the recurrence is affine with constant coefficient a = gamma*lambda, so a segment of
-//            length L maps carry c to  g_loc + a^L * c; only g_loc needs storing)
-//   pass 2: every segment composes the aggregates of the segments it depends on (Horner, <= S-1
-//           fused multiply-adds on values that sit in L2), then re-scans its rows with the true carry
-//           and writes the outputs.
-// Inputs are read twice, but in this regime they live in L2 (T*B*12 bytes << 126 MB).  Re-association
-// means results agree with the serial scan to ~1e-7 relative rather than bit for bit; the large-batch
-// TMA path above stays bit-exact.  SURVEY.md 8(f) item 2.
+// Small-batch regime (few columns, long T: e.g. the reference's own test shape T=1024, B=64,
+// tests/test_gae.py:10-11): single-launch T-split with look-back, scan_lookback.cuh.  One warp per
+// (segment, 32-column tile); the GAE recurrences have the constant coefficient gamma*lambda, so a segment
+// publishes only its zero-carry result and successors fold it with a^L.
 // ------------------------------------------------------------------------------------------------
-constexpr int kSplitThreads = 64;
-
-template <bool WRITE>
-__global__ void __launch_bounds__(kSplitThreads) gae_fwd_split(const float* __restrict__ value, int64_t ldv,
-                                                                const float* __restrict__ reward, int64_t ldr,
-                                                                const float* __restrict__ dtab,
-                                                                float* __restrict__ agg, float* __restrict__ adv,
-                                                                int64_t lda, int T, int B, int seg_len, float gamma,
-                                                                float factor) {
-    const int col = blockIdx.x * kSplitThreads + threadIdx.x;
-    const int s = blockIdx.y, S = gridDim.y;
-    if (col >= B) return;
-    const int t0 = s * seg_len, t1 = min(T, t0 + seg_len);
-    if (t0 >= T) {
-        if (!WRITE) agg[static_cast<int64_t>(s) * B + col] = 0.f;
-        return;
+struct GaeFwdLbFac {
+    const float* value;
+    int64_t ldv;
+    const float* dtab;
+    float* adv;
+    int64_t lda;
+    int col;
+    bool valid;
+    float gamma, factor;
+    using Body = GaeFwdBody<false>;
+    __device__ __forceinline__ Body make(int pass, int t_edge, float carry) const {  // t_edge = row after the segment
+        Body b;
+        b.valid = valid && pass == 1;
+        b.g = carry;
+        b.gamma = gamma;
+        b.factor = factor;
+        b.ld = lda;
+        b.m1 = b.m2 = 0.0;
+        b.p1 = b.p2 = 0.f;
+        b.adv = adv + static_cast<int64_t>(t_edge - 1) * lda + col;
+        b.v1 = valid ? __ldg(value + static_cast<int64_t>(t_edge) * ldv + col) : 0.f;
+        return b;
     }
-    float g = 0.f;
-    if (WRITE) {  // carry from the later segments: G = B_k + a^{len_k} * G, k = S-1 .. s+1
-        for (int k = S - 1; k > s; --k) {
-            const int len_k = min(T, (k + 1) * seg_len) - min(T, k * seg_len);
-            g = fmaf(powf(factor, static_cast<float>(len_k)), g, __ldcg(agg + static_cast<int64_t>(k) * B + col));
-        }
-    }
-    GaeFwdBody<> body;
-    body.valid = WRITE;
-    body.g = g;
-    body.gamma = gamma;
-    body.factor = factor;
-    body.ld = lda;
-    body.adv = adv + static_cast<int64_t>(t1 - 1) * lda + col;
-    body.v1 = __ldg(value + static_cast<int64_t>(t1) * ldv + col);
-    constexpr int U = 8;
-    int t = t1 - 1;
-    for (; t - (U - 1) >= t0; t -= U) {
-        float v[U], r[U];
-        float2 d[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            v[u] = __ldg(value + static_cast<int64_t>(t - u) * ldv + col);
-            r[u] = __ldg(reward + static_cast<int64_t>(t - u) * ldr + col);
-            d[u] = __ldg(reinterpret_cast<const float2*>(dtab) + t - u);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float x[2] = {v[u], r[u]};
-            const float dt[2] = {d[u].x, d[u].y};
-            body.step(t - u, x, dt);
-        }
-    }
-    for (; t >= t0; --t) {
-        const float x[2] = {__ldg(value + static_cast<int64_t>(t) * ldv + col),
-                            __ldg(reward + static_cast<int64_t>(t) * ldr + col)};
+    __device__ __forceinline__ void step(Body& b, int t, const float (&x)[2]) const {
         const float2 d = __ldg(reinterpret_cast<const float2*>(dtab) + t);
         const float dt[2] = {d.x, d.y};
-        body.step(t, x, dt);
+        b.step(t, x, dt);
     }
-    if (!WRITE) agg[static_cast<int64_t>(s) * B + col] = body.g;
+    static __device__ __forceinline__ float state(const Body& b) { return b.g; }
+    static __device__ __forceinline__ float coef(const Body&) { return 0.f; }
+    __device__ __forceinline__ void finish(Body&, int, int) const {}
+};
+
+__global__ void __launch_bounds__(kLbCols) gae_fwd_lookback(const float* __restrict__ value, int64_t ldv,
+                                                            const float* __restrict__ reward, int64_t ldr,
+                                                            const float* __restrict__ dtab, float* __restrict__ adv,
+                                                            int64_t lda, int T, int B, float gamma, float factor,
+                                                            float AL, int S, int L, int tiles, LbCtl* ctl,
+                                                            unsigned long long* words) {
+    __shared__ float smem[2 * kLbChunkRows * kLbCols];
+    const LbTile lt = lb_begin(ctl, tiles);
+    const int seg = S - 1 - lt.k;  // the scan runs backward in time: the last segment goes first
+    const int t0 = seg * L, t1 = min(T, t0 + L);
+    const int col = lt.tile * kLbCols + threadIdx.x;
+    const GaeFwdLbFac fac{value, ldv, dtab, adv, lda, col, col < B, gamma, factor};
+    const float* const in[2] = {value, reward};
+    const int64_t ld[2] = {ldv, ldr};
+    lb_segment<2, true, true>(fac, in, ld, t0, t1, col, col < B, lt, words, tiles * kLbCols, AL, smem);
+    lb_end(ctl, S * tiles, lt.epoch);
 }
 
-template <bool WRITE>
-__global__ void __launch_bounds__(kSplitThreads) gae_bwd_split(const float* __restrict__ grad_adv, int64_t ldg,
-                                                                const float* __restrict__ dtab,
-                                                                float* __restrict__ agg,
-                                                                float* __restrict__ grad_value, int64_t ldgv,
-                                                                float* __restrict__ grad_reward, int64_t ldgr, int T,
-                                                                int B, int seg_len, float gamma, float factor) {
-    const int col = blockIdx.x * kSplitThreads + threadIdx.x;
-    const int s = blockIdx.y;
-    if (col >= B) return;
-    const int t0 = s * seg_len, t1 = min(T, t0 + seg_len);
-    if (t0 >= T) {
-        if (!WRITE) agg[static_cast<int64_t>(s) * B + col] = 0.f;
-        return;
+struct GaeBwdLbFac {
+    const float* dtab;
+    float* gv;
+    int64_t ldgv;
+    float* gr;
+    int64_t ldgr;
+    int col, T;
+    bool valid;
+    float gamma, factor;
+    using Body = GaeBwdBody;
+    __device__ __forceinline__ Body make(int pass, int t_edge, float carry) const {  // t_edge = first row of the segment
+        Body b;
+        b.valid = valid && pass == 1;
+        b.gh = carry;
+        // dd of the previous row, exactly as the serial scan forms it: d_{t-1} * ghat_{t-1}
+        b.prev = t_edge > 0 ? __fmul_rn(__ldg(dtab + 2 * (t_edge - 1)), carry) : 0.f;
+        b.gamma = gamma;
+        b.factor = factor;
+        b.gv = gv + static_cast<int64_t>(t_edge) * ldgv + col;
+        b.gr = gr + static_cast<int64_t>(t_edge) * ldgr + col;
+        b.ld_gv = ldgv;
+        b.ld_gr = ldgr;
+        return b;
     }
-    float gh = 0.f;
-    if (WRITE) {  // carry from the earlier segments: ghat = agg_k + a^{len_k} * ghat, k = 0 .. s-1
-        for (int k = 0; k < s; ++k)
-            gh = fmaf(powf(factor, static_cast<float>(seg_len)), gh, __ldcg(agg + static_cast<int64_t>(k) * B + col));
-    }
-    GaeBwdBody body;
-    body.valid = WRITE;
-    body.gh = gh;
-    body.prev = t0 > 0 ? __fmul_rn(__ldg(dtab + 2 * (t0 - 1)), gh) : 0.f;  // dd_{t0-1} = d_{t0-1} * ghat_{t0-1}
-    body.gamma = gamma;
-    body.factor = factor;
-    body.gv = grad_value + static_cast<int64_t>(t0) * ldgv + col;
-    body.gr = grad_reward + static_cast<int64_t>(t0) * ldgr + col;
-    body.ld_gv = ldgv;
-    body.ld_gr = ldgr;
-    constexpr int U = 8;
-    int t = t0;
-    for (; t + U <= t1; t += U) {
-        float g[U];
-        float2 d[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            g[u] = __ldg(grad_adv + static_cast<int64_t>(t + u) * ldg + col);
-            d[u] = __ldg(reinterpret_cast<const float2*>(dtab) + t + u);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float x[1] = {g[u]};
-            const float dt[2] = {d[u].x, d[u].y};
-            body.step(t + u, x, dt);
-        }
-    }
-    for (; t < t1; ++t) {
-        const float x[1] = {__ldg(grad_adv + static_cast<int64_t>(t) * ldg + col)};
+    __device__ __forceinline__ void step(Body& b, int t, const float (&x)[1]) const {
         const float2 d = __ldg(reinterpret_cast<const float2*>(dtab) + t);
         const float dt[2] = {d.x, d.y};
-        body.step(t, x, dt);
+        b.step(t, x, dt);
     }
-    if (!WRITE) agg[static_cast<int64_t>(s) * B + col] = body.gh;
-    else if (t1 == T) *body.gv = __fmul_rn(gamma, body.prev);  // row T
+    static __device__ __forceinline__ float state(const Body& b) { return b.gh; }
+    static __device__ __forceinline__ float coef(const Body&) { return 0.f; }
+    __device__ __forceinline__ void finish(Body& b, int, int t1) const {
+        if (t1 == T && valid) st_stream(b.gv, __fmul_rn(gamma, b.prev));  // row T
+    }
+};
+
+__global__ void __launch_bounds__(kLbCols) gae_bwd_lookback(const float* __restrict__ grad_adv, int64_t ldg,
+                                                            const float* __restrict__ dtab, float* __restrict__ gv,
+                                                            int64_t ldgv, float* __restrict__ gr, int64_t ldgr, int T,
+                                                            int B, float gamma, float factor, float AL, int S, int L,
+                                                            int tiles, LbCtl* ctl, unsigned long long* words) {
+    __shared__ float smem[kLbChunkRows * kLbCols];
+    const LbTile lt = lb_begin(ctl, tiles);
+    const int t0 = lt.k * L, t1 = min(T, t0 + L);  // forward in time
+    const int col = lt.tile * kLbCols + threadIdx.x;
+    const GaeBwdLbFac fac{dtab, gv, ldgv, gr, ldgr, col, T, col < B, gamma, factor};
+    const float* const in[1] = {grad_adv};
+    const int64_t ld[1] = {ldg};
+    lb_segment<1, false, true>(fac, in, ld, t0, t1, col, col < B, lt, words, tiles * kLbCols, AL, smem);
+    lb_end(ctl, S * tiles, lt.epoch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -682,7 +661,7 @@ static int launch_bwd_tma_st(const float* grad_adv, int64_t ldg, const float* dt
 //   3: BT=64  TT=32 ST=3      4: BT=128 TT=8  ST=4     5: BT=64 TT=8  ST=6
 //   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     8: BT=256 TT=16 ST=3
 //  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     13: BT=32 TT=64 ST=6   14: BT=32 TT=16 ST=12
-//  20: T-split (small batch; opt-in)   99: generic (non-TMA) kernel
+//  21: single-launch T-split with look-back (automatic for B <= 4096, T >= 32; 20 = its old two-launch name)   99: generic (non-TMA) kernel
 //  30..34: TMA-staged OUTPUT as well (ScanPipeOut; results leave as (TT x BT) bulk stores):
 //  30: BT=256 TT=8 ST=4    31: BT=128 TT=16 ST=3    32: BT=256 TT=16 ST=3    33: BT=256 TT=4 ST=6    34: BT=256 TT=4 ST=5
 // (a TMA box dimension is limited to 256 elements, so BT <= 256)
@@ -699,63 +678,6 @@ static int pick_cfg(int64_t B, bool backward = false) {
     if (B >= 64 * sms) return 0;
     if (B >= 32 * sms) return 2;
     return 13;  // few column tiles: deeper row pipeline per CTA
-}
-
-// T-split geometry: S segments of seg_len rows so that tiles*S covers the machine about twice
-static bool split_geometry(int64_t T, int64_t B, int* S, int* seg_len) {
-    const int forced = tuning_config(HPC_RLL_OP_GAE);
-    if (forced >= 0 && forced != 20) return false;
-    // opt-in (config 20): measured on B200 (profiles/r01_gae_small_batch.md) the two launches halve the device
-    // time of long narrow problems (T=1024, B=64: 64 -> 41 us) but eager PyTorch calls are CPU-launch bound
-    // there, so it only pays under CUDA-graph replay
-    if (forced < 0) return false;
-    const int64_t tiles = (B + kSplitThreads - 1) / kSplitThreads;
-    int64_t s = (2 * static_cast<int64_t>(sm_count()) + tiles - 1) / tiles;
-    if (s > 32) s = 32;
-    if (s > T / 16) s = T / 16;
-    if (s < 2) return false;
-    int64_t len = (T + s - 1) / s;
-    len = (len + 7) / 8 * 8;
-    *seg_len = static_cast<int>(len);
-    *S = static_cast<int>((T + len - 1) / len);
-    return *S >= 2;
-}
-
-// scratch for the segment aggregates: S*B floats, cached per device and grown on demand.  Launches that
-// share it are ordered by the stream they run on; concurrent use from several streams of one device is
-// serialised by an event.
-namespace {
-struct SplitScratch {
-    float* buf = nullptr;
-    size_t cap = 0;
-    cudaEvent_t done = nullptr;
-};
-std::mutex g_split_mu;
-std::map<int, SplitScratch> g_split;
-}  // namespace
-
-// inside CUDA-graph capture the cross-stream event handshake is skipped (a graph replays on one stream
-// in order; warm up once before capturing so the scratch exists)
-
-static int split_scratch(size_t floats, cudaStream_t stream, SplitScratch** out) {
-    int dev = 0;
-    HPC_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(g_split_mu);
-    SplitScratch& sc = g_split[dev];
-    if (!sc.done) HPC_CUDA(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming));
-    if (sc.cap < floats) {
-        if (sc.buf) {
-            HPC_CUDA(cudaDeviceSynchronize());
-            cudaFree(sc.buf);
-        }
-        const size_t want = floats < (size_t(1) << 18) ? (size_t(1) << 18) : floats;
-        HPC_CUDA(cudaMalloc(&sc.buf, want * sizeof(float)));
-        sc.cap = want;
-    } else if (!stream_capturing(stream)) {
-        HPC_CUDA(cudaStreamWaitEvent(stream, sc.done, 0));  // previous user (possibly another stream) is done
-    }
-    *out = &sc;
-    return HPC_RLL_OK;
 }
 
 // One launch of the forward scan over `T` consecutive rows.  A whole problem has chunk == nullptr; a T-chunk of a
@@ -782,23 +704,21 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
     const float* v_next = chunk ? chunk->carry + B : value + T * ldv;
     if (chunk) dtab += 2 * chunk->t0;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
-    int S = 0, seg_len = 0;
-    if (!chunk && split_geometry(T, B, &S, &seg_len)) {
-        SplitScratch* sc = nullptr;
-        rc = split_scratch(static_cast<size_t>(S) * static_cast<size_t>(B), stream, &sc);
+    LbGeom lg;
+    if (!chunk && lookback_geometry(HPC_RLL_OP_GAE, T, B, &lg)) {  // small batch: single-launch T-split
+        LbScratch sc;
+        rc = lookback_scratch(lg, B, stream, &sc);
         if (rc) return rc;
-        const dim3 grid(static_cast<unsigned>((B + kSplitThreads - 1) / kSplitThreads), static_cast<unsigned>(S));
-        gae_fwd_split<false><<<grid, kSplitThreads, 0, stream>>>(value, ldv, reward, ldr, dtab, sc->buf, adv, lda,
-                                                                 static_cast<int>(T), static_cast<int>(B), seg_len, g, f);
-        gae_fwd_split<true><<<grid, kSplitThreads, 0, stream>>>(value, ldv, reward, ldr, dtab, sc->buf, adv, lda,
-                                                                static_cast<int>(T), static_cast<int>(B), seg_len, g, f);
-        count_launch(2);
+        const float AL = static_cast<float>(std::pow(gamma * lambda, static_cast<double>(lg.L)));
+        gae_fwd_lookback<<<static_cast<unsigned>(lg.S * lg.tiles), kLbCols, 0, stream>>>(
+            value, ldv, reward, ldr, dtab, adv, lda, static_cast<int>(T), static_cast<int>(B), g, f, AL, lg.S, lg.L,
+            lg.tiles, sc.ctl, sc.words);
+        count_launch();
         HPC_LAUNCH_CHECK();
-        if (!stream_capturing(stream)) HPC_CUDA(cudaEventRecord(sc->done, stream));
         return HPC_RLL_OK;
     }
     int cfg = pick_cfg(B);
-    if (cfg == 20) cfg = 13;
+    if (cfg == 20 || cfg == 21) cfg = 13;
     // the d_t slice of a stage is a 16-byte-aligned bulk copy: a chunk must start on an even row
     const bool tma = tma_ok_2d(value, B, ldv) && tma_ok_2d(reward, B, ldr) && aligned16(dtab);
     if (!tma) cfg = 99;
@@ -932,23 +852,21 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
     const int write_last = (!chunk || chunk->t0 + T == chunk->T_total) ? 1 : 0;
     if (chunk) dtab += 2 * chunk->t0;
     const float g = static_cast<float>(gamma), f = static_cast<float>(gamma * lambda);
-    int S = 0, seg_len = 0;
-    if (!chunk && split_geometry(T, B, &S, &seg_len)) {
-        SplitScratch* sc = nullptr;
-        rc = split_scratch(static_cast<size_t>(S) * static_cast<size_t>(B), stream, &sc);
+    LbGeom lg;
+    if (!chunk && lookback_geometry(HPC_RLL_OP_GAE, T, B, &lg)) {
+        LbScratch sc;
+        rc = lookback_scratch(lg, B, stream, &sc);
         if (rc) return rc;
-        const dim3 grid(static_cast<unsigned>((B + kSplitThreads - 1) / kSplitThreads), static_cast<unsigned>(S));
-        gae_bwd_split<false><<<grid, kSplitThreads, 0, stream>>>(grad_adv, ldg, dtab, sc->buf, gv, ldgv, gr, ldgr,
-                                                                 static_cast<int>(T), static_cast<int>(B), seg_len, g, f);
-        gae_bwd_split<true><<<grid, kSplitThreads, 0, stream>>>(grad_adv, ldg, dtab, sc->buf, gv, ldgv, gr, ldgr,
-                                                                static_cast<int>(T), static_cast<int>(B), seg_len, g, f);
-        count_launch(2);
+        const float AL = static_cast<float>(std::pow(gamma * lambda, static_cast<double>(lg.L)));
+        gae_bwd_lookback<<<static_cast<unsigned>(lg.S * lg.tiles), kLbCols, 0, stream>>>(
+            grad_adv, ldg, dtab, gv, ldgv, gr, ldgr, static_cast<int>(T), static_cast<int>(B), g, f, AL, lg.S, lg.L,
+            lg.tiles, sc.ctl, sc.words);
+        count_launch();
         HPC_LAUNCH_CHECK();
-        if (!stream_capturing(stream)) HPC_CUDA(cudaEventRecord(sc->done, stream));
         return HPC_RLL_OK;
     }
     int cfg = pick_cfg(B, true);
-    if (cfg == 20) cfg = 13;
+    if (cfg == 20 || cfg == 21) cfg = 13;
     if (!(tma_ok_2d(grad_adv, B, ldg) && aligned16(dtab))) cfg = 99;
     if (cfg >= 30 && cfg < 99 && !(tma_ok_2d(gv, B, ldgv) && tma_ok_2d(gr, B, ldgr))) cfg = 7;
 #define HPC_BWD(BT_, TT_, ST_) \
@@ -1065,14 +983,15 @@ int host_pipe_acquire(int dev, size_t floats, HostPipeLease* lease) {
     return HPC_RLL_OK;
 }
 
-// Stage heights of the T-chunked pipeline.  Measured on B200 / PCIe Gen5 (profiles/r02_e2e.md): every copy costs
-// ~10 us of DMA set-up on top of bytes/50 GB/s (duplex), i.e. ~30 us per stage and direction, while the first stage's
-// H2D copy and the last stage's D2H copy cannot overlap with anything (fill / drain).  Uniform 64-row stages (16 MB
-// copies) lose 2 x 0.87 ms to fill/drain; uniform 8-row stages lose 128 x 45 us to set-up.  So the heights RAMP:
-// R0, R0, 2 R0, 4 R0 ... Rmax, Rmax ... 4 R0, 2 R0, R0, R0 -- short stages where nothing overlaps, long ones in between.
-// The list is a palindrome: the backward walks it from row 0 up, the forward from row T down.
-// HPC_RLL_HOST_CHUNK_ROWS="r0:rmax" (or one number = uniform) overrides; rows are multiples of 4 (whole TMA boxes,
-// 16-byte aligned d_t slices); T % 4 extra rows ride in the stage that touches row T.
+// Stage heights of the T-chunked pipeline.  Measured on B200 / PCIe Gen5 (profiles/r02_e2e.md): in duplex the two copy
+// engines sustain ~45 (H2D) / ~47 (D2H) GB/s inside this pipeline (50 / 50 for two isolated 268 MB copies), every copy
+// costs ~10 us of set-up, and the first stage's H2D plus the last stage's D2H overlap with nothing.  Uniform stages of
+// 16 MB per tensor (64 rows at B=65536: 16 stages) were the best of {2..64 MB} at 17.8 ms per step against 16.1 ms for
+// the ideal duplex rate; ramped heights (short first / last stages) were tried and LOST (18.4 ms): the D2H engine,
+// the slower one, falls behind during the tall middle stages and drains alone at the end.  The generator still takes
+// "r0:rmax" for experiments (HPC_RLL_HOST_CHUNK_ROWS); one number = uniform.  Rows are multiples of 4 (whole TMA
+// boxes, 16-byte aligned d_t slices); T % 4 extra rows ride in the stage that touches row T.  The list is a
+// palindrome: the backward walks it from row 0 up, the forward from row T down.
 std::vector<int64_t> host_schedule(int64_t T, int64_t B) {
     static const std::pair<long long, long long> forced = [] {
         const char* e = getenv("HPC_RLL_HOST_CHUNK_ROWS");
@@ -1083,8 +1002,8 @@ std::vector<int64_t> host_schedule(int64_t T, int64_t B) {
     }();
     const int64_t row_bytes = 4 * (B > 0 ? B : 1);
     auto round4 = [](int64_t r) { return r < 4 ? int64_t(4) : (r / 4) * 4; };
-    int64_t r0 = round4(forced.first >= 4 ? forced.first : (int64_t(2) << 20) / row_bytes);
-    int64_t rmax = round4(forced.second >= 4 ? forced.second : (int64_t(32) << 20) / row_bytes);
+    int64_t r0 = round4(forced.first >= 4 ? forced.first : (int64_t(16) << 20) / row_bytes);
+    int64_t rmax = round4(forced.second >= 4 ? forced.second : r0);
     if (rmax < r0) rmax = r0;
     const int64_t T4 = (T / 4) * 4, rem = T - T4;
     std::vector<int64_t> sizes;
@@ -1145,6 +1064,21 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
     HPC_CUDA(cudaMemcpyAsync(carry_f + Bs, h_value + static_cast<size_t>(T) * Bs, Bs * sizeof(float),
                              cudaMemcpyHostToDevice, hp.s_h2d));
     HPC_CUDA(cudaMemsetAsync(carry_b, 0, 2 * Bs * sizeof(float), hp.s_h2d));
+    // HPC_RLL_HOST_TRACE=1: per-stage timeline (ms since the first copy) on stderr -- a diagnosis aid, off by default
+    static const bool trace = [] {
+        const char* e = getenv("HPC_RLL_HOST_TRACE");
+        return e && atoi(e) != 0;
+    }();
+    static const int debug_skip = [] {  // bit0: no kernels, bit1: no D2H, bit2: no H2D (timing experiments only)
+        const char* e = getenv("HPC_RLL_HOST_DEBUG_SKIP");
+        return e ? atoi(e) : 0;
+    }();
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(static_cast<size_t>(nC) * 4 + 1);
+        for (auto& e : tev) HPC_CUDA(cudaEventCreate(&e));
+        HPC_CUDA(cudaEventRecord(tev[nC * 4], hp.s_h2d));
+    }
     for (int64_t i = 0; i < nC; ++i) {
         const int s = static_cast<int>(i % HostPipe::kSlots);
         float* d_value = hp.buf + s * slot;
@@ -1160,15 +1094,20 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
         const size_t bbytes = static_cast<size_t>(brows) * Bs * sizeof(float);
         // ---- host -> device (waits until the kernels of the stage that used this slot before have read it)
         if (i >= HostPipe::kSlots) HPC_CUDA(cudaStreamWaitEvent(hp.s_h2d, hp.ev_k[s], 0));
+        if (trace) HPC_CUDA(cudaEventRecord(tev[i * 4 + 0], hp.s_h2d));
+        if (!(debug_skip & 4)) {
         HPC_CUDA(cudaMemcpyAsync(d_value, h_value + static_cast<size_t>(f0) * Bs, fbytes, cudaMemcpyHostToDevice, hp.s_h2d));
         HPC_CUDA(cudaMemcpyAsync(d_reward, h_reward + static_cast<size_t>(f0) * Bs, fbytes, cudaMemcpyHostToDevice, hp.s_h2d));
         if (bwd)
             HPC_CUDA(cudaMemcpyAsync(d_gadv, h_gadv + static_cast<size_t>(b0) * Bs, bbytes, cudaMemcpyHostToDevice, hp.s_h2d));
+        }
         HPC_CUDA(cudaEventRecord(hp.ev_h[s], hp.s_h2d));
+        if (trace) HPC_CUDA(cudaEventRecord(tev[i * 4 + 1], hp.s_h2d));
         // ---- kernels (wait for the inputs, and for the D2H copies that drained this slot's outputs)
         HPC_CUDA(cudaStreamWaitEvent(hp.s_k, hp.ev_h[s], 0));
         if (i >= HostPipe::kSlots) HPC_CUDA(cudaStreamWaitEvent(hp.s_k, hp.ev_d[s], 0));
         GaeChunk cf{T, f0, carry_f};
+        if (!(debug_skip & 1)) {
         rc = gae_forward_impl(d_value, B, d_reward, B, d_adv, B, frows, B, gamma, lambda, hp.s_k, &cf);
         if (rc) return rc;
         if (bwd) {
@@ -1176,19 +1115,32 @@ static int gae_host_impl(const float* h_value, const float* h_reward, const floa
             rc = gae_backward_impl(d_gadv, B, d_gvalue, B, d_greward, B, brows, B, gamma, lambda, hp.s_k, &cb);
             if (rc) return rc;
         }
+        }
         HPC_CUDA(cudaEventRecord(hp.ev_k[s], hp.s_k));
+        if (trace) HPC_CUDA(cudaEventRecord(tev[i * 4 + 2], hp.s_k));
         // ---- device -> host
         HPC_CUDA(cudaStreamWaitEvent(hp.s_d2h, hp.ev_k[s], 0));
+        if (!(debug_skip & 2))
         HPC_CUDA(cudaMemcpyAsync(h_adv + static_cast<size_t>(f0) * Bs, d_adv, fbytes, cudaMemcpyDeviceToHost, hp.s_d2h));
-        if (bwd) {
+        if (bwd && !(debug_skip & 2)) {
             const size_t gvbytes = bbytes + (b0 + brows == T ? Bs * sizeof(float) : 0);  // + row T at the end
             HPC_CUDA(cudaMemcpyAsync(h_gvalue + static_cast<size_t>(b0) * Bs, d_gvalue, gvbytes, cudaMemcpyDeviceToHost, hp.s_d2h));
             HPC_CUDA(cudaMemcpyAsync(h_greward + static_cast<size_t>(b0) * Bs, d_greward, bbytes, cudaMemcpyDeviceToHost, hp.s_d2h));
         }
         HPC_CUDA(cudaEventRecord(hp.ev_d[s], hp.s_d2h));
+        if (trace) HPC_CUDA(cudaEventRecord(tev[i * 4 + 3], hp.s_d2h));
     }
     HPC_CUDA(cudaEventRecord(hp.done, hp.s_d2h));
     HPC_CUDA(cudaEventSynchronize(hp.done));
+    if (trace) {
+        fprintf(stderr, "stage rows  h2d_begin  h2d_end  kernels_end  d2h_end   (ms)\n");
+        for (int64_t i = 0; i < nC; ++i) {
+            float t[4];
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[nC * 4], tev[i * 4 + k]);
+            fprintf(stderr, "%5lld %4lld  %8.3f %8.3f %8.3f %8.3f\n", (long long)i, (long long)sizes[i], t[0], t[1], t[2], t[3]);
+        }
+        for (auto& e : tev) cudaEventDestroy(e);
+    }
     return HPC_RLL_OK;
 }
 

@@ -1,0 +1,106 @@
+// scan_lookback.cu -- host side of the single-launch T-split (scan_lookback.cuh): when to use it, and its scratch.
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "scan_lookback.cuh"
+
+namespace hpcrll {
+
+// Geometry and automatic rule, from measurements on B200 (profiles/r02_small_batch.md).  The column-scan kernels walk
+// T as one dependent chain per thread: ~25 ns per step and direction whatever B is (T=1024: ~25 us per kernel for every
+// B <= 4096).  A look-back launch costs ~8 us of fixed latency (launch, one load round trip, publish/fold, store), and
+// its segments should fit ONE shared-memory chunk (32 rows) so that nothing is loaded twice and the two passes are 32
+// steps each.  Hence: segments of 32 rows (64+ only when T > 2048, since at most kLbMaxSeg segments are folded), and
+// the T-split is taken automatically when T >= 512 (below that the serial chain is already shorter than the fixed
+// cost) and B <= 4096 (above, the column tiles alone fill the machine).  tuning config 21 forces the look-back path for
+// any shape that splits, every other forced config disables it.
+bool lookback_geometry(int op, int64_t T, int64_t B, LbGeom* g) {
+    const int forced = tuning_config(op);
+    if (forced >= 0 && forced != 21) return false;
+    if (forced < 0 && (B > 4096 || T < 512)) return false;
+    if (T < 32 || B <= 0) return false;
+    const int64_t tiles = (B + kLbCols - 1) / kLbCols;
+    int64_t L = kLbChunkRows;
+    int64_t S = (T + L - 1) / L;
+    if (S > kLbMaxSeg) {
+        L = ((T + kLbMaxSeg - 1) / kLbMaxSeg + 7) / 8 * 8;
+        S = (T + L - 1) / L;
+    }
+    if (S < 2) return false;
+    g->S = static_cast<int>(S);
+    g->L = static_cast<int>(L);
+    g->tiles = static_cast<int>(tiles);
+    return true;
+}
+
+namespace {
+struct Entry {
+    LbScratch sc;
+    uint64_t last_use;
+};
+std::mutex g_mu;
+std::map<std::pair<int, cudaStream_t>, Entry> g_scratch;
+uint64_t g_tick = 0;
+constexpr size_t kMaxEntries = 64;
+
+bool capturing(cudaStream_t stream) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone;
+}
+}  // namespace
+
+// One scratch per (device, stream): kernels that share it are ordered by the stream.  Created (cudaMalloc + blocking
+// memset, epoch = 1) on first use, so do one warm-up call per stream before capturing a CUDA graph; it is grown, never
+// shrunk, and only freed (after a device synchronise, never during capture) when more than 64 streams have come by.
+int lookback_scratch(const LbGeom& g, int64_t B, cudaStream_t stream, LbScratch* out) {
+    (void)B;
+    int dev = 0;
+    HPC_CUDA(cudaGetDevice(&dev));
+    const size_t need = static_cast<size_t>(g.S) * static_cast<size_t>(g.tiles) * kLbCols * 2;
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto key = std::make_pair(dev, stream);
+    auto it = g_scratch.find(key);
+    if (it != g_scratch.end() && it->second.sc.cap_words >= need) {
+        it->second.last_use = ++g_tick;
+        *out = it->second.sc;
+        return HPC_RLL_OK;
+    }
+    HPC_REQUIRE(!capturing(stream),
+                "small-batch scan: scratch for this stream must exist before CUDA-graph capture (run one warm-up call)");
+    if (it != g_scratch.end()) {  // grow
+        HPC_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(it->second.sc.ctl);
+        g_scratch.erase(it);
+    } else if (g_scratch.size() >= kMaxEntries) {
+        auto lru = g_scratch.begin();
+        for (auto i = g_scratch.begin(); i != g_scratch.end(); ++i)
+            if (i->first.first == dev && (lru->first.first != dev || i->second.last_use < lru->second.last_use)) lru = i;
+        if (lru->first.first == dev) {
+            HPC_CUDA(cudaDeviceSynchronize());
+            cudaFree(lru->second.sc.ctl);
+            g_scratch.erase(lru);
+        }
+    }
+    size_t cap = need < (size_t(1) << 15) ? (size_t(1) << 15) : need;  // >= 256 KB of words: most shapes never regrow
+    void* p = nullptr;
+    const size_t bytes = 256 + cap * sizeof(unsigned long long);
+    HPC_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    LbCtl init{0u, 0u, 1u, 0u};
+    if (e == cudaSuccess) e = cudaMemcpy(p, &init, sizeof(init), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return set_error(HPC_RLL_ECUDA, "small-batch scan: scratch initialisation failed: %s", cudaGetErrorString(e));
+    }
+    Entry en;
+    en.sc.ctl = static_cast<LbCtl*>(p);
+    en.sc.words = reinterpret_cast<unsigned long long*>(static_cast<char*>(p) + 256);
+    en.sc.cap_words = cap;
+    en.last_use = ++g_tick;
+    g_scratch[key] = en;
+    *out = en.sc;
+    return HPC_RLL_OK;
+}
+
+}  // namespace hpcrll

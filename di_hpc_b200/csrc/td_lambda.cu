@@ -14,6 +14,7 @@
 // (without the upstream gradient).  Backward = scale by the upstream gradient (device scalar).
 // Bytes/step: fwd 8 (+4 weight) in + 4 out, bwd 4 in + 4 out.
 #include "reduce.cuh"
+#include "scan_lookback.cuh"
 #include "scan_pipe.cuh"
 
 namespace hpcrll {
@@ -68,6 +69,71 @@ __global__ void __launch_bounds__(BT + 32) td_lambda_fwd_tma(const __grid_consta
     double v[1] = {body.valid ? body.acc : 0.0};
     block_sum<1>(v, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = v[0];
+}
+
+// small batches: single-launch T-split with look-back (scan_lookback.cuh); constant coefficient gamma*lambda (the
+// reset at t = T-1 sits in the first segment scanned, which has no predecessor)
+template <int NIN>
+struct TdlLbFac {
+    const float* value;
+    float* grad_buf;
+    int B, T, col;
+    bool valid;
+    float gamma, disc, gmd, neg_inv_n;
+    double* partial;  // this CTA's slot
+    using Body = TdLambdaBody<NIN>;
+    __device__ __forceinline__ Body make(int pass, int t_edge, float carry) const {
+        Body b;
+        b.valid = valid && pass == 1;
+        b.ret = carry;
+        b.gamma = gamma;
+        b.disc = disc;
+        b.gmd = gmd;
+        b.neg_inv_n = neg_inv_n;
+        b.acc = 0.0;
+        b.ld = B;
+        b.t_last = T - 1;
+        b.gbuf = grad_buf + static_cast<int64_t>(t_edge - 1) * B + col;
+        b.v1 = valid ? __ldg(value + static_cast<int64_t>(t_edge) * B + col) : 0.f;
+        return b;
+    }
+    __device__ __forceinline__ void step(Body& b, int t, const float (&x)[NIN]) const {
+        const float none[1] = {0.f};
+        b.step(t, x, none);
+    }
+    static __device__ __forceinline__ float state(const Body& b) { return b.ret; }
+    static __device__ __forceinline__ float coef(const Body&) { return 0.f; }
+    __device__ __forceinline__ void finish(Body& b, int, int) const {
+        double v = valid ? b.acc : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) *partial = v;
+    }
+};
+
+template <int NIN>
+__global__ void __launch_bounds__(kLbCols) td_lambda_fwd_lookback(const float* __restrict__ value,
+                                                                  const float* __restrict__ reward,
+                                                                  const float* __restrict__ weight,
+                                                                  float* __restrict__ grad_buf,
+                                                                  double* __restrict__ partials, int T, int B, float gamma,
+                                                                  float disc, float gmd, float neg_inv_n, float AL, int S,
+                                                                  int L, int tiles, LbCtl* ctl, unsigned long long* words) {
+    __shared__ float smem[NIN * kLbChunkRows * kLbCols];
+    const LbTile lt = lb_begin(ctl, tiles);
+    const int seg = S - 1 - lt.k;
+    const int t0 = seg * L, t1 = min(T, t0 + L);
+    const int col = lt.tile * kLbCols + threadIdx.x;
+    const TdlLbFac<NIN> fac{value, grad_buf, B, T, col, col < B, gamma, disc, gmd, neg_inv_n, partials + lt.vid};
+    const float* in[NIN];
+    int64_t ld[NIN];
+    in[0] = value;
+    in[1] = reward;
+    if (NIN == 3) in[NIN - 1] = weight;
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) ld[k] = B;
+    lb_segment<NIN, true, true>(fac, in, ld, t0, t1, col, col < B, lt, words, tiles * kLbCols, AL, smem);
+    lb_end(ctl, S * tiles, lt.epoch);
 }
 
 // generic fallback (no TMA alignment requirements): one thread per column
@@ -134,7 +200,10 @@ static int launch_tdl_tma(const float* value, const float* reward, const float* 
     return HPC_RLL_OK;
 }
 
-size_t td_lambda_workspace_bytes(int64_t B) { return sizeof(double) * static_cast<size_t>((B + 31) / 32 + 8); }
+// per-CTA loss partials: one per column tile, or one per (segment, tile) of the small-batch T-split (<= 4*SMs + tiles)
+size_t td_lambda_workspace_bytes(int64_t B) {
+    return sizeof(double) * static_cast<size_t>((B + 31) / 32 + 4 * sm_count() + 72);
+}
 
 }  // namespace hpcrll
 
@@ -161,10 +230,28 @@ int hpc_rll_td_lambda_forward(const float* value, const float* reward, const flo
     int nblocks = 0;
     const bool tma = tma_ok_2d(value, B, B) && tma_ok_2d(reward, B, B) && (!weight || tma_ok_2d(weight, B, B));
     int cfg = tuning_config(HPC_RLL_OP_TD_LAMBDA);
+    LbGeom lg;
+    const bool lookback = lookback_geometry(HPC_RLL_OP_TD_LAMBDA, T, B, &lg);
     if (!tma) cfg = 99;
-    if (cfg < 0) cfg = B >= 128 * static_cast<int64_t>(sm_count()) ? 1 : (B >= 4096 ? 0 : 2);
+    if (cfg < 0 || cfg == 21) cfg = B >= 128 * static_cast<int64_t>(sm_count()) ? 1 : (B >= 4096 ? 0 : 2);
     int rc = HPC_RLL_OK;
-    if (cfg == 99) {
+    if (lookback) {
+        LbScratch sc;
+        rc = lookback_scratch(lg, B, stream, &sc);
+        if (rc) return rc;
+        nblocks = lg.S * lg.tiles;
+        const float AL = powf(disc, static_cast<float>(lg.L));
+        if (weight)
+            td_lambda_fwd_lookback<3><<<static_cast<unsigned>(nblocks), kLbCols, 0, stream>>>(
+                value, reward, weight, grad_buf, partials, static_cast<int>(T), static_cast<int>(B), g, disc, gmd, nin, AL,
+                lg.S, lg.L, lg.tiles, sc.ctl, sc.words);
+        else
+            td_lambda_fwd_lookback<2><<<static_cast<unsigned>(nblocks), kLbCols, 0, stream>>>(
+                value, reward, weight, grad_buf, partials, static_cast<int>(T), static_cast<int>(B), g, disc, gmd, nin, AL,
+                lg.S, lg.L, lg.tiles, sc.ctl, sc.words);
+        count_launch();
+        HPC_LAUNCH_CHECK();
+    } else if (cfg == 99) {
         const unsigned grid = static_cast<unsigned>((B + 127) / 128);
         nblocks = static_cast<int>(grid);
         if (weight)

@@ -12,6 +12,7 @@
 // Forward = upgo_rows_fwd (streaming log-softmax gather -> metric (T,B)) + upgo_scan (ScanPipe over
 // value/reward/rho/metric with the {0,1} coefficient carried in registers; emits coef = -adv/n and the
 // loss partials) + finaliser.  Backward = shared softmax-gradient row kernel (recompute from logits).
+#include "scan_lookback.cuh"
 #include "scan_pipe.cuh"
 #include "softmax_rows.cuh"
 
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(256) upgo_rows_fwd_loop(const float* __restric
 
 struct UpgoBody {
     float ret, v1, v2, r1, neg_inv_n;
+    float a_last;  // coefficient of the last step (0 or 1): used by the T-split look-back
     double acc;
     float* coef;  // running pointer, t descending
     int64_t ld;
@@ -107,8 +109,10 @@ struct UpgoBody {
         const float v0 = x[0], r = x[1];
         if (t == t_last) {
             ret = __fadd_rn(r, v1);
+            a_last = 0.f;
         } else {
             const float l = __fadd_rn(r1, v2) >= v1 ? 1.f : 0.f;
+            a_last = l;
             ret = __fadd_rn(__fadd_rn(r, __fmul_rn(l, ret)), __fmul_rn(1.f - l, v1));
         }
         const float adv = __fmul_rn(x[2], __fsub_rn(ret, v0));
@@ -143,6 +147,66 @@ __global__ void __launch_bounds__(BT + 32) upgo_scan_tma(const __grid_constant__
     double v[1] = {body.valid ? body.acc : 0.0};
     block_sum<1>(v, red);
     if (threadIdx.x == 0) partials[blockIdx.x] = v[0];
+}
+
+// small batches: single-launch T-split with look-back (scan_lookback.cuh).  The coefficient is the 0/1 "keep following
+// the trajectory" flag, so a segment publishes (prod a_t, zero-carry return); with a_t in {0,1} the composition is exact.
+struct UpgoLbFac {
+    const float* value;
+    const float* reward;
+    float* coef_out;
+    int B, T, col;
+    bool valid;
+    float neg_inv_n;
+    double* partial;
+    using Body = UpgoBody;
+    __device__ __forceinline__ Body make(int pass, int t_edge, float carry) const {
+        Body b;
+        b.valid = valid && pass == 1;
+        b.ret = carry;
+        b.neg_inv_n = neg_inv_n;
+        b.a_last = 1.f;
+        b.acc = 0.0;
+        b.ld = B;
+        b.t_last = T - 1;
+        b.coef = coef_out + static_cast<int64_t>(t_edge - 1) * B + col;
+        b.v1 = valid ? __ldg(value + static_cast<int64_t>(t_edge) * B + col) : 0.f;
+        // history the first step of the segment looks at: r_{t+1}, v_{t+2} (rows that exist whenever t_edge < T)
+        b.v2 = (valid && t_edge < T) ? __ldg(value + static_cast<int64_t>(t_edge + 1) * B + col) : 0.f;
+        b.r1 = (valid && t_edge < T) ? __ldg(reward + static_cast<int64_t>(t_edge) * B + col) : 0.f;
+        return b;
+    }
+    __device__ __forceinline__ void step(Body& b, int t, const float (&x)[4]) const {
+        const float none[1] = {0.f};
+        b.step(t, x, none);
+    }
+    static __device__ __forceinline__ float state(const Body& b) { return b.ret; }
+    static __device__ __forceinline__ float coef(const Body& b) { return b.a_last; }
+    __device__ __forceinline__ void finish(Body& b, int, int) const {
+        double v = valid ? b.acc : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) *partial = v;
+    }
+};
+
+__global__ void __launch_bounds__(kLbCols) upgo_scan_lookback(const float* __restrict__ value,
+                                                              const float* __restrict__ reward,
+                                                              const float* __restrict__ rho,
+                                                              const float* __restrict__ metric, float* __restrict__ coef,
+                                                              double* __restrict__ partials, int T, int B, float neg_inv_n,
+                                                              int S, int L, int tiles, LbCtl* ctl,
+                                                              unsigned long long* words) {
+    __shared__ float smem[4 * kLbChunkRows * kLbCols];
+    const LbTile lt = lb_begin(ctl, tiles);
+    const int seg = S - 1 - lt.k;
+    const int t0 = seg * L, t1 = min(T, t0 + L);
+    const int col = lt.tile * kLbCols + threadIdx.x;
+    const UpgoLbFac fac{value, reward, coef, B, T, col, col < B, neg_inv_n, partials + lt.vid};
+    const float* const in[4] = {value, reward, rho, metric};
+    const int64_t ld[4] = {B, B, B, B};
+    lb_segment<4, true, false>(fac, in, ld, t0, t1, col, col < B, lt, words, tiles * kLbCols, 1.f, smem);
+    lb_end(ctl, S * tiles, lt.epoch);
 }
 
 __global__ void __launch_bounds__(128) upgo_scan_generic(const float* __restrict__ value,
@@ -201,7 +265,8 @@ static inline int64_t align_up_(int64_t x, int64_t a) { return (x + a - 1) / a *
 
 // workspace: [metric (T*B f32) | partials]
 size_t upgo_workspace_bytes(int64_t T, int64_t B) {
-    return static_cast<size_t>(align_up_(T * B * 4, 256) + ((B + 31) / 32 + 16) * 8 + 256);
+    // partials: one per scan CTA -- column tiles, or (segment, tile) pairs of the small-batch T-split
+    return static_cast<size_t>(align_up_(T * B * 4, 256) + ((B + 31) / 32 + 4 * sm_count() + 80) * 8 + 256);
 }
 
 }  // namespace hpcrll
@@ -248,10 +313,22 @@ int hpc_rll_upgo_forward(const float* target_output, const float* rhos, const in
     const float nin = static_cast<float>(-inv_n);
     const bool tma = tma_ok_2d(bootstrap_values, B, B) && tma_ok_2d(rewards, B, B) && tma_ok_2d(rhos, B, B);
     int cfg = tuning_config(HPC_RLL_OP_UPGO);
+    LbGeom lg;
+    const bool lookback = lookback_geometry(HPC_RLL_OP_UPGO, T, B, &lg);
     if (!tma) cfg = 99;
-    if (cfg < 0) cfg = B >= 64 * static_cast<int64_t>(sm_count()) ? 0 : 2;
+    if (cfg < 0 || cfg == 21) cfg = B >= 64 * static_cast<int64_t>(sm_count()) ? 0 : 2;
     int nblocks = 0, rc = HPC_RLL_OK;
-    if (cfg == 99) {
+    if (lookback) {
+        LbScratch sc;
+        rc = lookback_scratch(lg, B, stream, &sc);
+        if (rc) return rc;
+        nblocks = lg.S * lg.tiles;
+        upgo_scan_lookback<<<static_cast<unsigned>(nblocks), kLbCols, 0, stream>>>(
+            bootstrap_values, rewards, rhos, metric, coef, partials, static_cast<int>(T), static_cast<int>(B), nin, lg.S,
+            lg.L, lg.tiles, sc.ctl, sc.words);
+        count_launch();
+        HPC_LAUNCH_CHECK();
+    } else if (cfg == 99) {
         nblocks = static_cast<int>((B + 127) / 128);
         upgo_scan_generic<<<nblocks, 128, 0, stream>>>(bootstrap_values, rewards, rhos, metric, coef, partials,
                                                        static_cast<int>(T), static_cast<int>(B), nin);

@@ -17,6 +17,7 @@
 //                     data-dependent coefficient gamma*lambda*c_t; emits the two per-step coefficients
 //                     the backward needs (pg_coef = -adv*w/n, gv_buf = 2(v-ret)w/n) and loss partials
 // Backward = softmax-gradient row kernel (recomputes softmax from logits) + scale of gv_buf.
+#include "scan_lookback.cuh"
 #include "scan_pipe.cuh"
 #include "softmax_rows.cuh"
 
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd_loop(const float* __restr
 template <int NIN>
 struct VtraceBody {
     float item, v1, ret_next, gamma, factor, rc, cc, pc, inv_n;
+    float a_last;  // coefficient of the last step (gamma*lambda*c_t): the T-split look-back multiplies these up
     double acc_pg, acc_v;
     float* pg_coef;  // running pointers, t descending
     float* gv_buf;
@@ -192,7 +194,8 @@ struct VtraceBody {
         const float rho = fminf(is, rc), c = fminf(is, cc), rpg = fminf(is, pc);
         const float v0 = x[0], r = x[1];
         const float delta = __fmul_rn(rho, __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, v1)), v0));
-        item = __fadd_rn(delta, __fmul_rn(__fmul_rn(factor, c), item));
+        a_last = __fmul_rn(factor, c);
+        item = __fadd_rn(delta, __fmul_rn(a_last, item));
         const float ret = __fadd_rn(v0, item);
         const float adv = __fmul_rn(rpg, __fsub_rn(__fadd_rn(r, __fmul_rn(gamma, ret_next)), v0));
         ret_next = ret;
@@ -243,6 +246,90 @@ __global__ void __launch_bounds__(BT + 32) vtrace_scan_tma(const __grid_constant
         partials[blockIdx.x] = v[0];
         partials[nblocks + blockIdx.x] = v[1];
     }
+}
+
+// small batches: single-launch T-split with look-back (scan_lookback.cuh).  The coefficient gamma*lambda*min(IS, c_bar)
+// is data dependent, so a segment publishes (prod a_t, zero-carry item); ret_{t+1} at a boundary is v_{t+1} + item_{t+1}
+// formed with the same single rounding as in the serial scan.
+template <int NIN>
+struct VtraceLbFac {
+    const float* value;
+    float* pg_coef;
+    float* gv_buf;
+    int B, col;
+    bool valid;
+    float gamma, factor, rc, cc, pc, inv_n;
+    double* partial_pg;
+    double* partial_v;
+    using Body = VtraceBody<NIN>;
+    __device__ __forceinline__ Body make(int pass, int t_edge, float carry) const {
+        Body b;
+        b.valid = valid && pass == 1;
+        b.item = carry;
+        b.gamma = gamma;
+        b.factor = factor;
+        b.rc = rc;
+        b.cc = cc;
+        b.pc = pc;
+        b.inv_n = inv_n;
+        b.a_last = 1.f;
+        b.acc_pg = b.acc_v = 0.0;
+        b.ld = B;
+        b.pg_coef = pg_coef + static_cast<int64_t>(t_edge - 1) * B + col;
+        b.gv_buf = gv_buf + static_cast<int64_t>(t_edge - 1) * B + col;
+        b.v1 = valid ? __ldg(value + static_cast<int64_t>(t_edge) * B + col) : 0.f;
+        b.ret_next = __fadd_rn(b.v1, carry);  // ret_T := v_T (carry is 0 there, vtrace.py:70)
+        return b;
+    }
+    __device__ __forceinline__ void step(Body& b, int t, const float (&x)[NIN]) const {
+        const float none[1] = {0.f};
+        b.step(t, x, none);
+    }
+    static __device__ __forceinline__ float state(const Body& b) { return b.item; }
+    static __device__ __forceinline__ float coef(const Body& b) { return b.a_last; }
+    __device__ __forceinline__ void finish(Body& b, int, int) const {
+        double v0 = valid ? b.acc_pg : 0.0, v1 = valid ? b.acc_v : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        }
+        if (threadIdx.x == 0) {
+            *partial_pg = v0;
+            *partial_v = v1;
+        }
+    }
+};
+
+template <int NIN>
+__global__ void __launch_bounds__(kLbCols) vtrace_scan_lookback(const float* __restrict__ value,
+                                                                const float* __restrict__ reward,
+                                                                const float* __restrict__ is_in,
+                                                                const float* __restrict__ logp_in,
+                                                                const float* __restrict__ weight,
+                                                                float* __restrict__ pg_coef, float* __restrict__ gv_buf,
+                                                                double* __restrict__ partials, int nblocks, int T, int B,
+                                                                float gamma, float factor, float rc, float cc, float pc,
+                                                                float inv_n, int S, int L, int tiles, LbCtl* ctl,
+                                                                unsigned long long* words) {
+    __shared__ float smem[NIN * kLbChunkRows * kLbCols];
+    const LbTile lt = lb_begin(ctl, tiles);
+    const int seg = S - 1 - lt.k;
+    const int t0 = seg * L, t1 = min(T, t0 + L);
+    const int col = lt.tile * kLbCols + threadIdx.x;
+    const VtraceLbFac<NIN> fac{value, pg_coef, gv_buf, B,  col,           col < B, gamma, factor, rc, cc, pc, inv_n,
+                               partials + lt.vid, partials + nblocks + lt.vid};
+    const float* in[NIN];
+    int64_t ld[NIN];
+    in[0] = value;
+    in[1] = reward;
+    in[2] = is_in;
+    in[3] = logp_in;
+    if (NIN == 5) in[NIN - 1] = weight;
+#pragma unroll
+    for (int k = 0; k < NIN; ++k) ld[k] = B;
+    lb_segment<NIN, true, false>(fac, in, ld, t0, t1, col, col < B, lt, words, tiles * kLbCols, 1.f, smem);
+    lb_end(ctl, S * tiles, lt.epoch);
 }
 
 template <bool HAS_W>
@@ -319,7 +406,9 @@ static int launch_vtrace_scan(const float* value, const float* reward, const flo
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 // workspace layout: [IS (T*B f32) | logp (T*B f32) | partials (doubles)]
-static int64_t vtrace_partials_cap(int64_t B) { return static_cast<int64_t>(sm_count()) * 16 + 2 * ((B + 31) / 32) + 16; }
+// rows-kernel partials (<= 16 per SM) + two per scan CTA: column tiles, or (segment, tile) pairs of the small-batch
+// T-split (<= 4*SMs + tiles of them)
+static int64_t vtrace_partials_cap(int64_t B) { return static_cast<int64_t>(sm_count()) * 24 + 4 * ((B + 31) / 32) + 160; }
 size_t vtrace_workspace_bytes(int64_t T, int64_t B) {
     return static_cast<size_t>(align_up(T * B * 4, 256) * 2 + vtrace_partials_cap(B) * 8 + 256);
 }
@@ -384,12 +473,29 @@ int hpc_rll_vtrace_forward(const float* target_output, const float* behaviour_ou
     double* part2 = partials + grid1;
     const bool tma = tma_ok_2d(value, B, B) && tma_ok_2d(reward, B, B) && (!weight || tma_ok_2d(weight, B, B));
     int cfg = tuning_config(HPC_RLL_OP_VTRACE);
+    LbGeom lg;
+    const bool lookback = lookback_geometry(HPC_RLL_OP_VTRACE, T, B, &lg);
     if (!tma) cfg = 99;
-    if (cfg < 0) cfg = B >= 64 * static_cast<int64_t>(sm_count()) ? 0 : 2;
+    if (cfg < 0 || cfg == 21) cfg = B >= 64 * static_cast<int64_t>(sm_count()) ? 0 : 2;
     int nblocks2;
     int rc2 = HPC_RLL_OK;
     const float in = static_cast<float>(inv_n);
-    if (cfg == 99) {
+    if (lookback) {
+        LbScratch sc;
+        rc2 = lookback_scratch(lg, B, stream, &sc);
+        if (rc2) return rc2;
+        nblocks2 = lg.S * lg.tiles;
+        if (weight)
+            vtrace_scan_lookback<5><<<static_cast<unsigned>(nblocks2), kLbCols, 0, stream>>>(
+                value, reward, is_buf, logp_buf, weight, pg_coef, gv_buf, part2, nblocks2, static_cast<int>(T),
+                static_cast<int>(B), g, f, rc, cc, pc, in, lg.S, lg.L, lg.tiles, sc.ctl, sc.words);
+        else
+            vtrace_scan_lookback<4><<<static_cast<unsigned>(nblocks2), kLbCols, 0, stream>>>(
+                value, reward, is_buf, logp_buf, weight, pg_coef, gv_buf, part2, nblocks2, static_cast<int>(T),
+                static_cast<int>(B), g, f, rc, cc, pc, in, lg.S, lg.L, lg.tiles, sc.ctl, sc.words);
+        count_launch();
+        HPC_LAUNCH_CHECK();
+    } else if (cfg == 99) {
         nblocks2 = static_cast<int>((B + 127) / 128);
         if (weight)
             vtrace_scan_generic<true><<<nblocks2, 128, 0, stream>>>(value, reward, is_buf, logp_buf, weight, pg_coef,

@@ -33,6 +33,11 @@ def bind_to_device(device: int = None) -> int:
     return int(_abi.lib().hpc_rll_bind_thread_to_device(int(device)))
 
 
+def unbind() -> None:
+    """Undo ``bind_to_device``: the CPU affinity from before the first bind and the default memory policy."""
+    _abi.lib().hpc_rll_bind_thread_to_device(-1)
+
+
 def pinned_empty(shape, device: int = None) -> torch.Tensor:
     """A page-locked fp32 host tensor whose pages sit on the NUMA node of ``device`` (zero-filled by the first touch).
     The memory is owned by the library and released when the tensor's storage dies."""

@@ -128,9 +128,10 @@ int hpc_rll_gae_fwd_bwd_host(const float* h_value, const float* h_reward, const 
  * GPU's socket, or eight ranks push all their DMA traffic through one socket's DRAM and the inter-socket link.
  *   hpc_rll_device_numa_node     NUMA node of CUDA device `device` (sysfs numa_node of its PCI function), -1 unknown
  *   hpc_rll_bind_thread_to_device  restrict the CALLING thread to that node's CPUs (threads it spawns inherit it)
- *                                and prefer that node for its page allocations; returns the node or -1 (left as is)
- *   hpc_rll_host_alloc / _free   page-locked host memory whose pages were first touched on that node
- *                                (mmap + best-effort mbind + touch by node-pinned threads + cudaHostRegister) */
+ *                                and prefer that node for its page allocations; returns the node or -1 (left as is).
+ *                                device < 0 undoes it (affinity from before the first bind, default memory policy)
+ *   hpc_rll_host_alloc / _free   page-locked host memory (cudaHostAlloc) allocated and first touched while the calling
+ *                                thread is confined to that node (its affinity / policy are restored afterwards) */
 int hpc_rll_device_numa_node(int device);
 int hpc_rll_bind_thread_to_device(int device);
 void* hpc_rll_host_alloc(size_t bytes, int device);

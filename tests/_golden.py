@@ -46,3 +46,16 @@ def rel_err(a, b):
     if a.size == 0:
         return 0.0
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+def grad_err(a, b):
+    """max|a-b| / max|b|: gradients of mean-type losses carry 1/(T*B) (or 1/B), so the floor of 1 in ``rel_err`` would
+    make a 1e-5 bar vacuous for them -- they are compared relative to their own largest entry instead."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if a.size == 0:
+        return 0.0
+    scale = float(np.max(np.abs(b)))
+    if scale == 0.0:
+        return float(np.max(np.abs(a)))
+    return float(np.max(np.abs(a - b)) / scale)

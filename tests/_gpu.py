@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests._golden import rel_err  # noqa: F401
+from tests._golden import grad_err, rel_err  # noqa: F401
 
 
 def need_cuda():

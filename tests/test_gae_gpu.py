@@ -2,8 +2,9 @@
 
 Tolerances: forward and backward are element-wise chains evaluated in the oracle's exact fp32
 operation order, so the column-scan kernels must be BIT-EXACT against oracle_f32 (and the forward
-against origin's own fp32 output in the golden fixtures).  The opt-in T-split kernels (config 20) re-associate
-the recurrence across segments: 2e-6 norm-relative there.
+against origin's own fp32 output in the golden fixtures).  Small batches (B <= 4096, T >= 512) automatically take the
+single-launch T-split with look-back (scan_lookback.cuh, config 21; automatic for T >= 512), which re-associates the recurrence across
+segment boundaries: 2e-6 norm-relative there, and the same shape forced through the column scan is bit-exact.
 Gradients vs origin autograd (different summation structure): 1e-5 norm-relative (north_star)."""
 import numpy as np
 import pytest
@@ -16,12 +17,13 @@ from tests._gpu import dev, host, need_cuda, rng
 pytestmark = pytest.mark.gpu
 
 SHAPES = [(1024, 64), (128, 128), (1, 5), (37, 3), (100, 260), (17, 1028), (64, 1), (33, 4), (250, 4096),
-          (16, 128), (15, 132), (1000, 7), (129, 2048), (513, 100), (2048, 36),
+          (16, 128), (15, 132), (1000, 7), (129, 2048), (513, 100), (2048, 36), (1024, 4096), (3000, 33), (40, 70), (31, 64),
           (64, 65536), (7, 40000)]  # wide batches: the TMA-staged-output kernels (ragged T and column tiles)
 
 
 def uses_split(T, B):
-    return False  # T-split is opt-in (config 20); the automatic path is always the bit-exact column scan
+    """mirror of lookback_geometry (csrc/scan_lookback.cu): automatic for B <= 4096 and T >= 512"""
+    return B <= 4096 and T >= 512
 
 
 def same(got, want, exact):
@@ -79,9 +81,9 @@ def test_gae_vs_golden(name):
     assert rel_err(gr, c.grad("reward", 64)) <= 1e-5
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 13, 14, 20, 30, 31, 32, 33, 34, 99])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 13, 14, 21, 30, 31, 32, 33, 34, 99])
 def test_gae_every_kernel_config(cfg):
-    """All tile configurations (and the non-TMA kernel) must give identical bits; 20 = T-split."""
+    """All tile configurations (and the non-TMA kernel) must give identical bits; 21 = T-split with look-back."""
     need_cuda()
     from di_hpc_b200 import _abi
     g = rng(77 + cfg)
@@ -95,9 +97,9 @@ def test_gae_every_kernel_config(cfg):
     finally:
         _abi.set_config(0, -1)
     ob = orc.gae_backward(gadv, 0.95, 0.9)
-    same(adv, orc.gae_forward(value, reward, 0.95, 0.9), cfg != 20)
-    same(gv, ob["value"], cfg != 20)
-    same(gr, ob["reward"], cfg != 20)
+    same(adv, orc.gae_forward(value, reward, 0.95, 0.9), cfg != 21)
+    same(gv, ob["value"], cfg != 21)
+    same(gr, ob["reward"], cfg != 21)
 
 
 def test_gae_strided_views():

@@ -50,7 +50,7 @@ def test_names_gae_and_td_lambda():
     value, reward, weight = scan_inputs(rng(1), T, B)
     adv = z(T, B)
     H.GaeForward([dev(value), dev(reward)], [adv], 0.99, 0.97)
-    assert np.array_equal(host(adv), orc.gae_forward(value, reward, np.float32(0.99), np.float32(0.97)))
+    close(host(adv), orc.gae_forward(value, reward, np.float32(0.99), np.float32(0.97)), "adv")
     loss, gbuf, gval = z(1), z(T, B), z(T + 1, B)
     H.TdLambdaForward([dev(value), dev(reward), dev(weight)], [loss, gbuf], 0.9, 0.8)
     H.TdLambdaBackward([one() * 1.7, gbuf], [gval])
@@ -200,7 +200,7 @@ def test_reference_wrappers_gae_tdlambda():
     T, B = 1024, 64  # tests/test_gae.py:10-11, tests/test_tdlambda.py:10-11
     value, reward, weight = scan_inputs(g, T, B)
     adv = _ref("gae").GAE(T, B).cuda()(dev(value), dev(reward))
-    assert np.array_equal(host(adv), orc.gae_forward(value, reward, np.float32(0.99), np.float32(0.97)))
+    close(host(adv), orc.gae_forward(value, reward, np.float32(0.99), np.float32(0.97)), "adv")
     v = dev(value).requires_grad_(True)
     loss = _ref("td").TDLambda(T, B).cuda()(v, dev(reward), dev(weight))
     loss.backward()

@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import oracle as orc
-from tests._golden import Case, names, rel_err
+from tests._golden import Case, grad_err, names, rel_err
 from tests._gpu import dev, host, need_cuda, rng
 
 pytestmark = pytest.mark.gpu
@@ -16,6 +16,12 @@ TOL = 1e-5
 def close(got, want, what):
     e = rel_err(got, want)
     assert e <= TOL, "%s: rel err %.3e" % (what, e)
+
+
+def close_grad(got, want, what):
+    """gradients: relative to their own largest entry (they carry 1/n, see tests/_golden.grad_err)"""
+    e = grad_err(got, want)
+    assert e <= TOL, "%s: err / max|grad| = %.3e" % (what, e)
 
 
 # ----------------------------------------------------------------------------------------- vtrace
@@ -61,8 +67,8 @@ def test_vtrace_vs_oracle(T, B, N, use_w, hp):
                    inp["weight"], coef=coef, **hp)
     for k, name in enumerate(("policy_loss", "value_loss", "entropy_loss")):
         close(losses[k], o[name], name)
-    close(gt, o["grad_target_output"], "grad_target_output")
-    close(gv, o["grad_value"], "grad_value")
+    close_grad(gt, o["grad_target_output"], "grad_target_output")
+    close_grad(gv, o["grad_value"], "grad_value")
     assert np.all(gv[-1] == 0)
 
 
@@ -77,8 +83,8 @@ def test_vtrace_vs_golden(name):
     for prec in (32, 64):
         for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss")):
             close(losses[k], c.out(nm, prec), nm)
-        close(gt, c.grad("target_output", prec), "grad_target_output")
-        close(gv, c.grad("value", prec), "grad_value")
+        close_grad(gt, c.grad("target_output", prec), "grad_target_output")
+        close_grad(gv, c.grad("value", prec), "grad_value")
 
 
 @pytest.mark.parametrize("cfg", [0, 1, 2, 99])
@@ -96,8 +102,8 @@ def test_vtrace_scan_configs(cfg):
                    inp["weight"], coef=coef, **HP2)
     close(losses[0], o["policy_loss"], "pg")
     close(losses[1], o["value_loss"], "v")
-    close(gt, o["grad_target_output"], "gt")
-    close(gv, o["grad_value"], "gv")
+    close_grad(gt, o["grad_target_output"], "gt")
+    close_grad(gv, o["grad_value"], "gv")
 
 
 # ----------------------------------------------------------------------------------------- upgo
@@ -125,7 +131,7 @@ def test_upgo_vs_oracle(T, B, N):
     loss, gt = run_upgo(inp, -0.7)
     o = orc.upgo(inp["target_output"], inp["rhos"], inp["action"], inp["rewards"], inp["bootstrap_values"], -0.7)
     close(loss, o["loss"], "loss")
-    close(gt, o["grad_target_output"], "grad_target_output")
+    close_grad(gt, o["grad_target_output"], "grad_target_output")
 
 
 @pytest.mark.parametrize("name", names("upgo"))
@@ -136,7 +142,7 @@ def test_upgo_vs_golden(name):
     loss, gt = run_upgo(inp, c.attr("coef_loss"))
     for prec in (32, 64):
         close(loss, c.out("loss", prec), "loss")
-        close(gt, c.grad("target_output", prec), "grad_target_output")
+        close_grad(gt, c.grad("target_output", prec), "grad_target_output")
 
 
 # ----------------------------------------------------------------------------------------- ppo
@@ -178,8 +184,8 @@ def test_ppo_vs_oracle(B, N, use_w, clip, vclip, dual):
                 inp["return_"], inp["weight"], clip, vclip, dual, coef)
     for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss", "approx_kl", "clipfrac")):
         close(outs[k], o[nm], nm)
-    close(gl, o["grad_logits_new"], "grad_logits_new")
-    close(gv, o["grad_value_new"], "grad_value_new")
+    close_grad(gl, o["grad_logits_new"], "grad_logits_new")
+    close_grad(gv, o["grad_value_new"], "grad_value_new")
 
 
 @pytest.mark.parametrize("name", names("ppo"))
@@ -193,8 +199,8 @@ def test_ppo_vs_golden(name):
     for prec in (32, 64):
         for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss")):
             close(outs[k], c.out(nm, prec), nm)
-        close(gl, c.grad("logits_new", prec), "grad_logits_new")
-        close(gv, c.grad("value_new", prec), "grad_value_new")
+        close_grad(gl, c.grad("logits_new", prec), "grad_logits_new")
+        close_grad(gv, c.grad("value_new", prec), "grad_value_new")
     close(outs[3], c.out("approx_kl", 32), "approx_kl")
     close(outs[4], c.out("clipfrac", 32), "clipfrac")
 
@@ -230,7 +236,7 @@ def test_masked_actions_with_minus_inf_logits():
         close(losses[i], o[name], name)
     assert np.all(gt[:, :, k] == 0)
     close(np.delete(gt, k, axis=2), o["grad_target_output"], "grad_target_output")
-    close(gv, o["grad_value"], "grad_value")
+    close_grad(gv, o["grad_value"], "grad_value")
 
 
 # ----------------------------------------------------------------------------------------- row geometry sweep
@@ -252,15 +258,15 @@ def test_row_geometry_sweep(N):
                    inp["weight"], coef=coef, **HP2)
     for i, name in enumerate(("policy_loss", "value_loss", "entropy_loss")):
         close(losses[i], o[name], "vtrace " + name)
-    close(gt, o["grad_target_output"], "vtrace grad_target_output")
-    close(gv, o["grad_value"], "vtrace grad_value")
+    close_grad(gt, o["grad_target_output"], "vtrace grad_target_output")
+    close_grad(gv, o["grad_value"], "vtrace grad_value")
 
     up = dict(target_output=inp["target_output"], rhos=(g.random((T, B)) * 2).astype(np.float32), action=inp["action"],
               rewards=inp["reward"], bootstrap_values=inp["value"])
     loss, gt = run_upgo(up, -0.7)
     o = orc.upgo(up["target_output"], up["rhos"], up["action"], up["rewards"], up["bootstrap_values"], -0.7)
     close(loss, o["loss"], "upgo loss")
-    close(gt, o["grad_target_output"], "upgo grad_target_output")
+    close_grad(gt, o["grad_target_output"], "upgo grad_target_output")
 
     pp = ppo_inputs(g, 131, N, True)
     c3 = [1.0, 0.5, -0.01]
@@ -270,5 +276,44 @@ def test_row_geometry_sweep(N):
     for k, nm in enumerate(("policy_loss", "value_loss", "entropy_loss", "approx_kl")):
         close(outs[k], o[nm], "ppo " + nm)
     assert abs(outs[4] - o["clipfrac"]) <= 2.0 / 131 + 1e-6
-    close(gl, o["grad_logits_new"], "ppo grad_logits_new")
-    close(gvn, o["grad_value_new"], "ppo grad_value_new")
+    close_grad(gl, o["grad_logits_new"], "ppo grad_logits_new")
+    close_grad(gvn, o["grad_value_new"], "ppo grad_value_new")
+
+
+@pytest.mark.parametrize("T,B,N,use_w", [(1024, 64, 6, True), (100, 33, 16, False), (64, 4096, 4, True), (517, 130, 9, True)])
+def test_small_batch_tsplit_agrees_with_column_scan(T, B, N, use_w):
+    """V-trace / UPGO scans: the single-launch T-split with look-back (config 21, automatic for B <= 4096) against the
+    column-scan kernels (config 2) and the oracle on the same inputs; data-dependent coefficients (gamma*lambda*c_t,
+    the 0/1 UPGO flag) are multiplied up across segments.  Also run-to-run bit reproducibility of the T-split."""
+    need_cuda()
+    from di_hpc_b200 import _abi
+    g = rng(T + 31 * B + N)
+    inp = vtrace_inputs(g, T, B, N, use_w)
+    coef = [1.0, 0.5, -0.25]
+    up = dict(target_output=inp["target_output"], rhos=(g.random((T, B)) * 2).astype(np.float32), action=inp["action"],
+              rewards=inp["reward"], bootstrap_values=inp["value"])
+    res = {}
+    try:
+        for cfg in (21, 2, 21):
+            _abi.set_config(_abi.OP_VTRACE, cfg)
+            _abi.set_config(_abi.OP_UPGO, cfg)
+            res.setdefault(cfg, []).append((run_vtrace(inp, HP2, coef), run_upgo(up, -0.7)))
+    finally:
+        _abi.set_config(_abi.OP_VTRACE, -1)
+        _abi.set_config(_abi.OP_UPGO, -1)
+    o = orc.vtrace(inp["target_output"], inp["behaviour_output"], inp["action"], inp["value"], inp["reward"],
+                   inp["weight"], coef=coef, **HP2)
+    ou = orc.upgo(up["target_output"], up["rhos"], up["action"], up["rewards"], up["bootstrap_values"], -0.7)
+    for cfg in (21, 2):
+        (losses, gt, gv), (ul, ugt) = res[cfg][0]
+        for i, name in enumerate(("policy_loss", "value_loss", "entropy_loss")):
+            close(losses[i], o[name], "cfg %d vtrace %s" % (cfg, name))
+        close_grad(gt, o["grad_target_output"], "cfg %d vtrace grad_target_output" % cfg)
+        close_grad(gv, o["grad_value"], "cfg %d vtrace grad_value" % cfg)
+        close(ul, ou["loss"], "cfg %d upgo loss" % cfg)
+        close_grad(ugt, ou["grad_target_output"], "cfg %d upgo grad" % cfg)
+    a, b = res[21]
+    assert a[0][0] == b[0][0] and np.array_equal(a[0][1], b[0][1]) and np.array_equal(a[0][2], b[0][2])
+    assert a[1][0] == b[1][0] and np.array_equal(a[1][1], b[1][1])
+    # UPGO's coefficient is 0/1: composing segments is exact, the T-split must give the column scan's bits
+    assert np.array_equal(res[21][0][1][1], res[2][0][1][1])

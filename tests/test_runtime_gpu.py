@@ -26,7 +26,7 @@ def test_side_stream_and_noncontiguous_inputs():
         adv = GAE(T, B)(vt, dev(reward))
         loss = TDLambda(T, B)(vt, dev(reward))
     s.synchronize()
-    assert np.array_equal(host(adv), orc.gae_forward(value, reward))
+    assert rel_err(host(adv), orc.gae_forward(value, reward)) <= 2e-6  # B <= 4096: T-split path (re-associated)
     assert rel_err(float(loss.item()), orc.td_lambda(value, reward)["loss"]) <= 1e-5
 
 
@@ -62,9 +62,18 @@ def test_cuda_graph_capture_and_replay():
     torch.cuda.synchronize()
     graph.replay()
     torch.cuda.synchronize()
-    assert np.array_equal(host(adv), orc.gae_forward(host(value), host(reward)))
+    # B = 2048: the small-batch T-split kernels (epoch-tagged look-back scratch must survive graph replay)
+    assert rel_err(host(adv), orc.gae_forward(host(value), host(reward))) <= 2e-6
     ob = orc.gae_backward(host(gadv))
-    assert np.array_equal(host(gv), ob["value"]) and np.array_equal(host(gr), ob["reward"])
+    assert rel_err(host(gv), ob["value"]) <= 2e-6 and rel_err(host(gr), ob["reward"]) <= 2e-6
+    for _ in range(3):  # replay again with new data: stale aggregates of the previous replay must not be taken
+        value.copy_(dev(g.standard_normal((T + 1, B), dtype=np.float32)))
+        gadv.copy_(dev(g.standard_normal((T, B), dtype=np.float32)))
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert rel_err(host(adv), orc.gae_forward(host(value), host(reward))) <= 2e-6
+        assert rel_err(host(gv), orc.gae_backward(host(gadv))["value"]) <= 2e-6
     assert rel_err(float(loss.item()), orc.td_lambda(host(value), host(reward))["loss"]) <= 1e-5
 
 
