@@ -13,12 +13,12 @@ namespace hpcrll {
 // its segments should fit ONE shared-memory chunk (32 rows) so that nothing is loaded twice and the two passes are 32
 // steps each.  Hence: segments of 32 rows (64+ only when T > 2048, since at most kLbMaxSeg segments are folded), and
 // the T-split is taken automatically when T >= 512 (below that the serial chain is already shorter than the fixed
-// cost) and B <= 4096 (above, the column tiles alone fill the machine).  tuning config 21 forces the look-back path for
+// cost) and B <= 2048 (measured at T=1024, fwd+bwd under graph replay: B=64 21 us vs 49, B=1024 29 vs 51, B=4096 66 vs 53).  tuning config 21 forces the look-back path for
 // any shape that splits, every other forced config disables it.
 bool lookback_geometry(int op, int64_t T, int64_t B, LbGeom* g) {
     const int forced = tuning_config(op);
     if (forced >= 0 && forced != 21) return false;
-    if (forced < 0 && (B > 4096 || T < 512)) return false;
+    if (forced < 0 && (B > 2048 || T < 512)) return false;
     if (T < 32 || B <= 0) return false;
     const int64_t tiles = (B + kLbCols - 1) / kLbCols;
     int64_t L = kLbChunkRows;

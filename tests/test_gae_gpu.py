@@ -2,7 +2,7 @@
 
 Tolerances: forward and backward are element-wise chains evaluated in the oracle's exact fp32
 operation order, so the column-scan kernels must be BIT-EXACT against oracle_f32 (and the forward
-against origin's own fp32 output in the golden fixtures).  Small batches (B <= 4096, T >= 512) automatically take the
+against origin's own fp32 output in the golden fixtures).  Small batches (B <= 2048, T >= 512) automatically take the
 single-launch T-split with look-back (scan_lookback.cuh, config 21; automatic for T >= 512), which re-associates the recurrence across
 segment boundaries: 2e-6 norm-relative there, and the same shape forced through the column scan is bit-exact.
 Gradients vs origin autograd (different summation structure): 1e-5 norm-relative (north_star)."""
@@ -22,8 +22,8 @@ SHAPES = [(1024, 64), (128, 128), (1, 5), (37, 3), (100, 260), (17, 1028), (64, 
 
 
 def uses_split(T, B):
-    """mirror of lookback_geometry (csrc/scan_lookback.cu): automatic for B <= 4096 and T >= 512"""
-    return B <= 4096 and T >= 512
+    """mirror of lookback_geometry (csrc/scan_lookback.cu): automatic for B <= 2048 and T >= 512"""
+    return B <= 2048 and T >= 512
 
 
 def same(got, want, exact):
