@@ -664,6 +664,7 @@ static int launch_bwd_tma_st(const float* grad_adv, int64_t ldg, const float* dt
 //  21: single-launch T-split with look-back (automatic for B <= 4096, T >= 32; 20 = its old two-launch name)   99: generic (non-TMA) kernel
 //  30..34: TMA-staged OUTPUT as well (ScanPipeOut; results leave as (TT x BT) bulk stores):
 //  30: BT=256 TT=8 ST=4    31: BT=128 TT=16 ST=3    32: BT=256 TT=16 ST=3    33: BT=256 TT=4 ST=6    34: BT=256 TT=4 ST=5
+//  35: BT=64 TT=16 ST=4    36: BT=128 TT=8 ST=5     37: BT=64 TT=8 ST=6       38: BT=128 TT=4 ST=8   (mid-size batches)
 // (a TMA box dimension is limited to 256 elements, so BT <= 256)
 // forced values >= 100 encode different kernels per direction: forward = v % 100, backward = v / 100
 static int pick_cfg(int64_t B, bool backward = false) {
@@ -748,6 +749,10 @@ static int gae_forward_impl(const float* value, int64_t ldv, const float* reward
         case 32: HPC_FWD_ST(256, 16, 3);
         case 33: HPC_FWD_ST(256, 4, 6);
         case 34: HPC_FWD_ST(256, 4, 5);
+        case 35: HPC_FWD_ST(64, 16, 4);
+        case 36: HPC_FWD_ST(128, 8, 5);
+        case 37: HPC_FWD_ST(64, 8, 6);
+        case 38: HPC_FWD_ST(128, 4, 8);
         default: break;
     }
 #undef HPC_FWD
@@ -802,10 +807,10 @@ static int gae_forward_moments_impl(const float* value, const float* reward, flo
         case 7: case 8: case 10: case 11: case 30: case 32: case 33: case 34:
             rc = launch_fwd_tma<256, 8, 4, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
             break;
-        case 1: case 4: case 6: case 31:
+        case 1: case 4: case 6: case 31: case 36: case 38:
             rc = launch_fwd_tma<128, 16, 3, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
             break;
-        case 0: case 3: case 5:
+        case 0: case 3: case 5: case 35: case 37:
             rc = launch_fwd_tma<64, 16, 3, true>(value, B, reward, B, dtab, adv, B, T, B, g, f, stream, partials, &nblocks);
             break;
         case 2: case 14:
@@ -893,6 +898,10 @@ static int gae_backward_impl(const float* grad_adv, int64_t ldg, float* gv, int6
         case 32: HPC_BWD_ST(256, 16, 3);
         case 33: HPC_BWD_ST(256, 4, 6);
         case 34: HPC_BWD_ST(256, 4, 5);
+        case 35: HPC_BWD_ST(64, 16, 4);
+        case 36: HPC_BWD_ST(128, 8, 5);
+        case 37: HPC_BWD_ST(64, 8, 6);
+        case 38: HPC_BWD_ST(128, 4, 8);
         default: break;
     }
 #undef HPC_BWD

@@ -2,6 +2,7 @@
 #include <map>
 #include <mutex>
 #include <utility>
+#include <vector>
 
 #include "scan_lookback.cuh"
 
@@ -51,8 +52,35 @@ bool capturing(cudaStream_t stream) {
 }  // namespace
 
 // One scratch per (device, stream): kernels that share it are ordered by the stream.  Created (cudaMalloc + blocking
-// memset, epoch = 1) on first use, so do one warm-up call per stream before capturing a CUDA graph; it is grown, never
-// shrunk, and only freed (after a device synchronise, never during capture) when more than 64 streams have come by.
+// memset, epoch = 1) on first use of a stream.  That is not possible while the stream is being CAPTURED (allocation and
+// the legacy-stream memset are illegal then), and PyTorch's graph helpers (`torch.cuda.graph`,
+// `torch.cuda.make_graphed_callables`) capture on an internal stream the caller never sees -- so every eager call also
+// keeps a few zeroed SPARE scratches per device in stock, and a capturing stream that has none adopts a spare.  The usual
+// "run the step eagerly once before capturing" is therefore all a caller has to do.  Scratches are grown, never shrunk,
+// and only freed (after a device synchronise, never during capture) when more than 64 streams have come by.
+namespace {
+constexpr size_t kSpareWords = size_t(1) << 18;  // 2 MB: covers every automatic shape (S <= 64, B <= 2048)
+constexpr int kSparesPerDevice = 4;
+std::map<int, std::vector<LbScratch>> g_spares;
+
+int new_scratch(size_t cap, LbScratch* out) {
+    void* p = nullptr;
+    const size_t bytes = 256 + cap * sizeof(unsigned long long);
+    HPC_CUDA(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    LbCtl init{0u, 0u, 1u, 0u};
+    if (e == cudaSuccess) e = cudaMemcpy(p, &init, sizeof(init), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return set_error(HPC_RLL_ECUDA, "small-batch scan: scratch initialisation failed: %s", cudaGetErrorString(e));
+    }
+    out->ctl = static_cast<LbCtl*>(p);
+    out->words = reinterpret_cast<unsigned long long*>(static_cast<char*>(p) + 256);
+    out->cap_words = cap;
+    return HPC_RLL_OK;
+}
+}  // namespace
+
 int lookback_scratch(const LbGeom& g, int64_t B, cudaStream_t stream, LbScratch* out) {
     (void)B;
     int dev = 0;
@@ -66,8 +94,22 @@ int lookback_scratch(const LbGeom& g, int64_t B, cudaStream_t stream, LbScratch*
         *out = it->second.sc;
         return HPC_RLL_OK;
     }
-    HPC_REQUIRE(!capturing(stream),
-                "small-batch scan: scratch for this stream must exist before CUDA-graph capture (run one warm-up call)");
+    if (capturing(stream)) {
+        auto& spares = g_spares[dev];
+        for (size_t i = 0; it == g_scratch.end() && i < spares.size(); ++i)
+            if (spares[i].cap_words >= need) {
+                Entry en;
+                en.sc = spares[i];
+                en.last_use = ++g_tick;
+                spares.erase(spares.begin() + static_cast<long>(i));
+                g_scratch[key] = en;
+                *out = en.sc;
+                return HPC_RLL_OK;
+            }
+        return set_error(HPC_RLL_EINVAL,
+                         "small-batch scan: no scratch for the capturing stream -- run the same call once eagerly "
+                         "(any stream) before capturing a CUDA graph");
+    }
     if (it != g_scratch.end()) {  // grow
         HPC_CUDA(cudaStreamSynchronize(stream));
         cudaFree(it->second.sc.ctl);
@@ -82,24 +124,19 @@ int lookback_scratch(const LbGeom& g, int64_t B, cudaStream_t stream, LbScratch*
             g_scratch.erase(lru);
         }
     }
-    size_t cap = need < (size_t(1) << 15) ? (size_t(1) << 15) : need;  // >= 256 KB of words: most shapes never regrow
-    void* p = nullptr;
-    const size_t bytes = 256 + cap * sizeof(unsigned long long);
-    HPC_CUDA(cudaMalloc(&p, bytes));
-    cudaError_t e = cudaMemset(p, 0, bytes);
-    LbCtl init{0u, 0u, 1u, 0u};
-    if (e == cudaSuccess) e = cudaMemcpy(p, &init, sizeof(init), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        cudaFree(p);
-        return set_error(HPC_RLL_ECUDA, "small-batch scan: scratch initialisation failed: %s", cudaGetErrorString(e));
-    }
     Entry en;
-    en.sc.ctl = static_cast<LbCtl*>(p);
-    en.sc.words = reinterpret_cast<unsigned long long*>(static_cast<char*>(p) + 256);
-    en.sc.cap_words = cap;
+    int rc = new_scratch(need < (size_t(1) << 15) ? (size_t(1) << 15) : need, &en.sc);
+    if (rc) return rc;
     en.last_use = ++g_tick;
     g_scratch[key] = en;
     *out = en.sc;
+    // keep spares in stock for streams that first show up while capturing (sized for this shape if it is larger)
+    auto& spares = g_spares[dev];
+    while (static_cast<int>(spares.size()) < kSparesPerDevice) {
+        LbScratch sp;
+        if (new_scratch(need > kSpareWords ? need : kSpareWords, &sp) != HPC_RLL_OK) break;
+        spares.push_back(sp);
+    }
     return HPC_RLL_OK;
 }
 

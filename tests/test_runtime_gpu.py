@@ -132,3 +132,37 @@ def test_empty_and_degenerate_sizes():
     rc = L.hpc_rll_td_lambda_forward(x.data_ptr(), x.data_ptr(), None, x.data_ptr(), x.data_ptr(), 0, 8, 0.9, 0.8, 0,
                                      ws.data_ptr(), ws.numel(), st)
     assert rc == 1 and b"positive" in L.hpc_rll_last_error()
+
+
+def test_make_graphed_callables_small_batch():
+    """The module-level answer to launch latency at small batches: PyTorch's own `torch.cuda.make_graphed_callables`
+    captures forward AND autograd backward of a drop-in module into CUDA graphs.  It captures on an internal stream, so
+    this exercises the look-back scratch adoption during capture (csrc/scan_lookback.cu) and the epoch re-arming across
+    replays, on the reference's own test shape (tests/test_gae.py:10-11, tests/test_tdlambda.py:10-11)."""
+    need_cuda()
+    from hpc_rll.rl_utils.gae import GAE
+    from hpc_rll.rl_utils.td import TDLambda
+    g = rng(9)
+    T, B = 1024, 64
+    sv = torch.randn(T + 1, B, device="cuda", requires_grad=True)
+    sr = torch.randn(T, B, device="cuda", requires_grad=True)
+    ggae = torch.cuda.make_graphed_callables(GAE(T, B), (sv, sr))
+    gtd = torch.cuda.make_graphed_callables(TDLambda(T, B), (sv.detach().clone().requires_grad_(True), sr.detach().clone()))
+    for _ in range(3):
+        value = g.standard_normal((T + 1, B), dtype=np.float32)
+        reward = g.standard_normal((T, B), dtype=np.float32)
+        gadv = g.standard_normal((T, B), dtype=np.float32)
+        v, r = dev(value).requires_grad_(True), dev(reward).requires_grad_(True)
+        adv = ggae(v, r)
+        adv.backward(dev(gadv))
+        torch.cuda.synchronize()
+        ob = orc.gae_backward(gadv)
+        assert rel_err(host(adv), orc.gae_forward(value, reward)) <= 2e-6
+        assert rel_err(host(v.grad), ob["value"]) <= 2e-6 and rel_err(host(r.grad), ob["reward"]) <= 2e-6
+        v2 = dev(value).requires_grad_(True)
+        loss = gtd(v2, dev(reward))
+        loss.backward()
+        torch.cuda.synchronize()
+        o = orc.td_lambda(value, reward)
+        assert rel_err(float(loss.item()), o["loss"]) <= 1e-5
+        assert float(np.max(np.abs(host(v2.grad) - o["grad_value"])) / np.max(np.abs(o["grad_value"]))) <= 1e-5

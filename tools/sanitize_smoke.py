@@ -73,9 +73,24 @@ def chunked_and_host():
     hp.gae_fwd_bwd_host(hv, hr, None)
 
 
+def small_batch_tsplit():
+    """round 2: the automatic small-batch path (T >= 512, B <= 2048) of all four scans, incl. a ragged last segment and
+    a column count that is not a multiple of the 32-column tile"""
+    for T, B, N in ((600, 70, 5), (1024, 64, 3)):
+        v, rew = r(T + 1, B).requires_grad_(True), r(T, B).requires_grad_(True)
+        torch.autograd.grad(GAE(T, B)(v, rew), [v, rew], grad_outputs=r(T, B))
+        torch.autograd.grad(TDLambda(T, B)(v, rew.detach(), torch.rand(T, B, device=D)), [v], grad_outputs=ONE)
+        t = r(T, B, N).requires_grad_(True)
+        a = torch.randint(0, N, (T, B), device=D)
+        l = VTrace(T, B, N)(t, r(T, B, N), a, v, rew.detach())
+        torch.autograd.grad(l.policy_loss + l.value_loss + l.entropy_loss, [t, v], grad_outputs=ONE)
+        torch.autograd.grad(UPGO(T, B, N)(t, torch.rand(T, B, device=D), a, rew.detach(), v.detach()), [t], grad_outputs=ONE)
+
+
 def main():
     wide_and_fused()
     chunked_and_host()
+    small_batch_tsplit()
     for T, B, N in ((37, 132, 6), (16, 260, 16), (9, 64, 40)):
         v, rew = r(T + 1, B).requires_grad_(True), r(T, B).requires_grad_(True)
         for cfg in (-1, 0, 2, 13, 21, 99):
@@ -83,13 +98,13 @@ def main():
             torch.autograd.grad(GAE(T, B)(v, rew), [v, rew], grad_outputs=r(T, B))
         _abi.set_config(0, -1)
         w = torch.rand(T, B, device=D)
-        for cfg in (-1, 99):
+        for cfg in (-1, 21, 99):  # 21 = single-launch T-split with look-back
             _abi.set_config(1, cfg)
             torch.autograd.grad(TDLambda(T, B)(v, rew.detach(), w), [v], grad_outputs=ONE)
         _abi.set_config(1, -1)
         t = r(T, B, N).requires_grad_(True)
         a = torch.randint(0, N, (T, B), device=D)
-        for cfg in (-1, 99):
+        for cfg in (-1, 21, 99):
             _abi.set_config(2, cfg)
             _abi.set_config(3, cfg)
             l = VTrace(T, B, N)(t, r(T, B, N), a, v, rew.detach(), w)
