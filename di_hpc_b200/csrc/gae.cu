@@ -676,7 +676,9 @@ static int pick_cfg(int64_t B, bool backward = false) {
     // boxes is 7-8 % faster than per-thread stores (forward 6.67 TB/s, backward 6.13 TB/s)
     if (B >= 256 * sms) return backward ? 33 : 34;
     if (B >= 128 * sms) return 1;
-    if (B >= 64 * sms) return 0;
+    // below ~19k columns the scan is bound by the T-step dependency chain, not by HBM: narrow tiles (more CTAs) win;
+    // at T=1024, B=16384 <32,32,3> takes 37 / 43 us against 47 / 50 us for <64,16,3> (profiles/r02_gae_mid_sweep.txt);
+    // the staged-output variants (31, 35-38) do not help here
     if (B >= 32 * sms) return 2;
     return 13;  // few column tiles: deeper row pipeline per CTA
 }
