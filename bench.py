@@ -430,6 +430,26 @@ def run_ours(args):
     def e2e_step():  # returns only after the results are in the host tensors
         hostapi.gae_fwd_bwd_host(hv, hr, hg, GAMMA, LAMBDA, out=hout)
 
+    # the link ceiling WITH ALL RANKS ACTIVE: every rank copies 268 MB each way at once, 4 times (GPUs that share a
+    # PCIe switch uplink or a socket's memory controllers slow each other down; this is the figure e2e can be judged by)
+    dbuf_in, dbuf_out = torch.empty(T, B, device=dev), torch.empty(T, B, device=dev)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def duplex_once():
+        with torch.cuda.stream(s_in):
+            dbuf_in.copy_(hr, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            hout[0].copy_(dbuf_out, non_blocking=True)
+
+    duplex_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        duplex_once()
+    barrier()
+    duplex_gbs = 4 * T * B * 4 / max_over_ranks(time.perf_counter() - t0, torch.float64) / 1e9
+    del dbuf_in, dbuf_out
+
     Ke = max(3, min(K, 10))
     for _ in range(2):
         e2e_step()
@@ -444,6 +464,8 @@ def run_ours(args):
     e2e = {"value": T * B * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": Ke,
            "gbs_each_way": h2d / (e2e_ms * 1e-3) / 1e9, "numa_node": numa_node,
+           "pcie_duplex_gbs_each_way_all_ranks_active": duplex_gbs,
+           "frac_of_that_duplex_rate": h2d / (e2e_ms * 1e-3) / 1e9 / duplex_gbs,
            "api": "di_hpc_b200.host.gae_fwd_bwd_host -> hpc_rll_gae_fwd_bwd_host (page-locked host tensors on the GPU's "
                   "NUMA node; T-chunked H2D / kernel / D2H carry pipeline)"}
     del hv, hr, hg, hout
