@@ -35,6 +35,7 @@ SIGNATURES = {
     "hpc_rll_gae_fwd_bwd_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_dbl, c_dbl]),
     "hpc_rll_gae_forward_chunk": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
     "hpc_rll_gae_backward_chunk": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_dbl, c_dbl, c_vp]),
+    "hpc_rll_debug_host_schedule": (c_i64, [c_i64, c_i64, c_vp, c_i64]),
     "hpc_rll_device_numa_node": (c_int, [c_int]),
     "hpc_rll_bind_thread_to_device": (c_int, [c_int]),
     "hpc_rll_host_alloc": (c_vp, [c_sz, c_int]),

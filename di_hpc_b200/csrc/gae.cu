@@ -1227,6 +1227,12 @@ int hpc_rll_gae_backward_chunk(const float* grad_adv, float* grad_value, float* 
     return gae_backward_impl(grad_adv, B, grad_value, B, grad_reward, B, rows, B, gamma, lambda, as_stream(stream), &c);
 }
 
+int64_t hpc_rll_debug_host_schedule(int64_t T, int64_t B, int64_t* rows, int64_t cap) {
+    const std::vector<int64_t> v = hpcrll::host_schedule(T, B);
+    for (size_t i = 0; i < v.size() && static_cast<int64_t>(i) < cap; ++i) rows[i] = v[i];
+    return static_cast<int64_t>(v.size());
+}
+
 int hpc_rll_gae_fwd_bwd_host(const float* h_value, const float* h_reward, const float* h_grad_adv, float* h_adv,
                              float* h_grad_value, float* h_grad_reward, int64_t T, int64_t B, double gamma,
                              double lambda) {

@@ -123,6 +123,10 @@ int hpc_rll_gae_fwd_bwd_host(const float* h_value, const float* h_reward, const 
                              float* h_grad_value, float* h_grad_reward, int64_t T, int64_t B, double gamma,
                              double lambda);
 
+/* test hook: the stage heights hpc_rll_gae_fwd_bwd_host would use for a (T,B) problem (host-only, no CUDA call);
+ * writes up to `cap` entries, returns the number of stages */
+int64_t hpc_rll_debug_host_schedule(int64_t T, int64_t B, int64_t* rows, int64_t cap);
+
 /* ---- host placement (NUMA) --------------------------------------------------------------------
  * A B200 box has its GPUs split over two CPU sockets; host buffers that feed a GPU over PCIe should live on that
  * GPU's socket, or eight ranks push all their DMA traffic through one socket's DRAM and the inter-socket link.

@@ -25,3 +25,8 @@ def test_reference_arm_prints_one_contract_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == j["value"] and "T=1024 B=65536" in cb["sample"]
     assert j["e2e"] == {"value": j["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "T=1024 B=65536" in j["config"]["workload"] and "model" not in j["config"]
+    # both arms print the SAME config (`same_config` was false because the workload strings differed)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert j["config"] == bench.config_of(1024, 65536, 1)
+    assert cb["reference_origin_context"]["forward_backward_s"] == 148.7  # hpc_rll.origin itself, build-container timing

@@ -129,6 +129,7 @@ def bench_ppo(B, N, iters):
     vn = rnd(B).requires_grad_(True)
     vo, adv, ret = rnd(B), rnd(B), rnd(B)
     m = PPO(B, N)
+    m.lazy_info = True  # approx_kl / clipfrac as LazyScalars: no blocking D2H copy per call
 
     def fwd():
         l, _ = m(ln, lo, a, vn, vo, adv, ret)
