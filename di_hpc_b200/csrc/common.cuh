@@ -16,6 +16,8 @@
 #include <cstdarg>
 #include <cstdio>
 
+#include <nvtx3/nvToolsExt.h>  // header-only in CUDA 12: ranges cost a few ns unless a profiler is attached
+
 #include "../../include/hpc_rll_b200.h"
 
 namespace hpcrll {
@@ -42,6 +44,16 @@ void clear_error();
 #define HPC_LAUNCH_CHECK() HPC_CUDA(cudaGetLastError())
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// one NVTX range per C-ABI entry point (the reference has only TRACE/printf debugging,
+// include/hpc/rll/cuda/common.h:17-20); shows up in nsys / ncu --nvtx timelines as "hpc_rll:<entry>"
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define HPC_NVTX(name) ::hpcrll::NvtxRange nvtx_range__("hpc_rll:" name)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7u) == 0; }

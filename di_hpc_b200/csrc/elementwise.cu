@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) axpby_kernel(const float* __restrict__ a,
 
 extern "C" int hpc_rll_axpby(const float* a, const float* x, const float* b, const float* y, float* out, int64_t n,
                              void* stream) {
+    HPC_NVTX("axpby");
     using namespace hpcrll;
     HPC_REQUIRE(n >= 0, "axpby: negative n");
     if (n == 0) return HPC_RLL_OK;

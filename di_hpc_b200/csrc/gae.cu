@@ -1161,12 +1161,14 @@ extern "C" {
 
 int hpc_rll_gae_forward(const float* value, const float* reward, float* adv, int64_t T, int64_t B, double gamma,
                         double lambda, void* stream) {
+    HPC_NVTX("gae_forward");
     return hpcrll::gae_forward_impl(value, B, reward, B, adv, B, T, B, gamma, lambda, hpcrll::as_stream(stream));
 }
 
 int hpc_rll_gae_forward_moments(const float* value, const float* reward, float* adv, double* moments, int64_t T,
                                 int64_t B, double gamma, double lambda, void* workspace, size_t workspace_bytes,
                                 void* stream) {
+    HPC_NVTX("gae_forward_moments");
     using namespace hpcrll;
     HPC_REQUIRE(T > 0 && B > 0, "gae_forward_moments: T and B must be positive (T=%lld B=%lld)", (long long)T,
                 (long long)B);
@@ -1178,6 +1180,7 @@ int hpc_rll_gae_forward_moments(const float* value, const float* reward, float* 
 }
 
 int hpc_rll_adv_stats(const double* moments, int64_t count, float* stats, void* stream) {
+    HPC_NVTX("adv_stats");
     using namespace hpcrll;
     HPC_REQUIRE(moments && stats, "adv_stats: null pointer");
     adv_stats_kernel<<<1, 1, 0, as_stream(stream)>>>(moments, static_cast<double>(count), stats);
@@ -1188,6 +1191,7 @@ int hpc_rll_adv_stats(const double* moments, int64_t count, float* stats, void* 
 
 int hpc_rll_gae_backward(const float* grad_adv, float* grad_value, float* grad_reward, int64_t T, int64_t B,
                          double gamma, double lambda, void* stream) {
+    HPC_NVTX("gae_backward");
     return hpcrll::gae_backward_impl(grad_adv, B, grad_value, B, grad_reward, B, T, B, gamma, lambda,
                                      hpcrll::as_stream(stream));
 }
@@ -1195,6 +1199,7 @@ int hpc_rll_gae_backward(const float* grad_adv, float* grad_value, float* grad_r
 int hpc_rll_gae_forward_ld(const float* value, int64_t ld_value, const float* reward, int64_t ld_reward,
                            float* adv, int64_t ld_adv, int64_t T, int64_t B, double gamma, double lambda,
                            void* stream) {
+    HPC_NVTX("gae_forward_ld");
     return hpcrll::gae_forward_impl(value, ld_value, reward, ld_reward, adv, ld_adv, T, B, gamma, lambda,
                                     hpcrll::as_stream(stream));
 }
@@ -1202,12 +1207,14 @@ int hpc_rll_gae_forward_ld(const float* value, int64_t ld_value, const float* re
 int hpc_rll_gae_backward_ld(const float* grad_adv, int64_t ld_grad_adv, float* grad_value, int64_t ld_grad_value,
                             float* grad_reward, int64_t ld_grad_reward, int64_t T, int64_t B, double gamma,
                             double lambda, void* stream) {
+    HPC_NVTX("gae_backward_ld");
     return hpcrll::gae_backward_impl(grad_adv, ld_grad_adv, grad_value, ld_grad_value, grad_reward, ld_grad_reward,
                                      T, B, gamma, lambda, hpcrll::as_stream(stream));
 }
 
 int hpc_rll_gae_forward_chunk(const float* value, const float* reward, float* adv, float* carry, int64_t T_total,
                               int64_t t0, int64_t rows, int64_t B, double gamma, double lambda, void* stream) {
+    HPC_NVTX("gae_forward_chunk");
     using namespace hpcrll;
     HPC_REQUIRE(carry != nullptr, "gae_forward_chunk: null carry");
     HPC_REQUIRE(t0 >= 0 && rows >= 0 && t0 + rows <= T_total, "gae_forward_chunk: rows [%lld, %lld) outside T=%lld",
@@ -1219,6 +1226,7 @@ int hpc_rll_gae_forward_chunk(const float* value, const float* reward, float* ad
 int hpc_rll_gae_backward_chunk(const float* grad_adv, float* grad_value, float* grad_reward, float* carry,
                                int64_t T_total, int64_t t0, int64_t rows, int64_t B, double gamma, double lambda,
                                void* stream) {
+    HPC_NVTX("gae_backward_chunk");
     using namespace hpcrll;
     HPC_REQUIRE(carry != nullptr, "gae_backward_chunk: null carry");
     HPC_REQUIRE(t0 >= 0 && rows >= 0 && t0 + rows <= T_total, "gae_backward_chunk: rows [%lld, %lld) outside T=%lld",
@@ -1236,6 +1244,7 @@ int64_t hpc_rll_debug_host_schedule(int64_t T, int64_t B, int64_t* rows, int64_t
 int hpc_rll_gae_fwd_bwd_host(const float* h_value, const float* h_reward, const float* h_grad_adv, float* h_adv,
                              float* h_grad_value, float* h_grad_reward, int64_t T, int64_t B, double gamma,
                              double lambda) {
+    HPC_NVTX("gae_fwd_bwd_host");
     return hpcrll::gae_host_impl(h_value, h_reward, h_grad_adv, h_adv, h_grad_value, h_grad_reward, T, B, gamma,
                                  lambda);
 }

@@ -137,6 +137,7 @@ int hpc_rll_bind_thread_to_device(int device) {
 }
 
 void* hpc_rll_host_alloc(size_t bytes, int device) {
+    HPC_NVTX("host_alloc");
     using namespace hpcrll;
     if (bytes == 0) {
         set_error(HPC_RLL_EINVAL, "host_alloc: zero bytes");

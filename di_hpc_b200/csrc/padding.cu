@@ -147,11 +147,13 @@ extern "C" {
 
 int hpc_rll_pad_batch(const float* const* src, float* const* dst, int32_t* const* mask, const int32_t* shapes,
                       const int32_t* padded, int64_t n, int value, void* stream) {
+    HPC_NVTX("pad_batch");
     return hpcrll::pad_batch(src, dst, mask, shapes, padded, n, value, false, hpcrll::as_stream(stream));
 }
 
 int hpc_rll_unpad_batch(const float* const* src, float* const* dst, const int32_t* shapes, const int32_t* padded,
                         int64_t n, void* stream) {
+    HPC_NVTX("unpad_batch");
     return hpcrll::pad_batch(src, dst, nullptr, shapes, padded, n, 0, true, hpcrll::as_stream(stream));
 }
 

@@ -333,6 +333,7 @@ int hpc_rll_ppo_forward(const float* logits_new, const float* logits_old, const 
                         const float* weight, float* out5, float* pol_coef, float* val_coef, int64_t B, int64_t N,
                         double clip_ratio, int use_value_clip, double dual_clip, int64_t global_B, void* workspace,
                         size_t workspace_bytes, void* stream) {
+    HPC_NVTX("ppo_forward");
     return hpcrll::ppo_forward_impl(logits_new, logits_old, action, value_new, value_old, adv, return_, weight, nullptr,
                                     out5, pol_coef, val_coef, B, N, clip_ratio, use_value_clip, dual_clip, global_B,
                                     workspace, workspace_bytes, stream);
@@ -344,6 +345,7 @@ int hpc_rll_ppo_forward_norm(const float* logits_new, const float* logits_old, c
                              float* val_coef, int64_t B, int64_t N, double clip_ratio, int use_value_clip,
                              double dual_clip, int64_t global_B, void* workspace, size_t workspace_bytes,
                              void* stream) {
+    HPC_NVTX("ppo_forward_norm");
     using namespace hpcrll;
     HPC_REQUIRE(adv_stats, "ppo_forward_norm: adv_stats is null (use hpc_rll_ppo_forward for pre-normalised adv)");
     return ppo_forward_impl(logits_new, logits_old, action, value_new, value_old, adv, return_, weight, adv_stats, out5,
@@ -355,6 +357,7 @@ int hpc_rll_ppo_backward(const float* grad_policy_loss, const float* grad_value_
                          const float* logits_new, const int64_t* action, const float* weight, const float* pol_coef,
                          const float* val_coef, float* grad_logits_new, float* grad_value_new, int64_t B, int64_t N,
                          int64_t global_B, void* stream_) {
+    HPC_NVTX("ppo_backward");
     using namespace hpcrll;
     cudaStream_t stream = as_stream(stream_);
     HPC_REQUIRE(B > 0 && N > 0, "ppo_backward: sizes must be positive");

@@ -212,6 +212,7 @@ extern "C" {
 int hpc_rll_td_lambda_forward(const float* value, const float* reward, const float* weight, float* loss,
                               float* grad_buf, int64_t T, int64_t B, double gamma, double lambda,
                               int64_t global_B, void* workspace, size_t workspace_bytes, void* stream_) {
+    HPC_NVTX("td_lambda_forward");
     using namespace hpcrll;
     cudaStream_t stream = as_stream(stream_);
     HPC_REQUIRE(T > 0 && B > 0, "td_lambda_forward: T and B must be positive (T=%lld B=%lld)", (long long)T,
@@ -288,6 +289,7 @@ int hpc_rll_td_lambda_forward(const float* value, const float* reward, const flo
 
 int hpc_rll_td_lambda_backward(const float* grad_loss, const float* grad_buf, float* grad_value, int64_t T,
                                int64_t B, void* stream_) {
+    HPC_NVTX("td_lambda_backward");
     using namespace hpcrll;
     HPC_REQUIRE(T > 0 && B > 0, "td_lambda_backward: T and B must be positive");
     HPC_REQUIRE(grad_loss && grad_buf && grad_value, "td_lambda_backward: null pointer");

@@ -277,6 +277,7 @@ int hpc_rll_upgo_forward(const float* target_output, const float* rhos, const in
                          const float* rewards, const float* bootstrap_values, float* loss, float* coef, int64_t T,
                          int64_t B, int64_t N, int64_t global_B, void* workspace, size_t workspace_bytes,
                          void* stream_) {
+    HPC_NVTX("upgo_forward");
     using namespace hpcrll;
     cudaStream_t stream = as_stream(stream_);
     HPC_REQUIRE(T > 0 && B > 0 && N > 0, "upgo_forward: sizes must be positive (T=%lld B=%lld N=%lld)", (long long)T,
@@ -352,6 +353,7 @@ int hpc_rll_upgo_forward(const float* target_output, const float* rhos, const in
 int hpc_rll_upgo_backward(const float* grad_loss, const float* target_output, const int64_t* action,
                           const float* coef, float* grad_target_output, int64_t T, int64_t B, int64_t N,
                           void* stream_) {
+    HPC_NVTX("upgo_backward");
     using namespace hpcrll;
     HPC_REQUIRE(T > 0 && B > 0 && N > 0, "upgo_backward: sizes must be positive");
     HPC_REQUIRE(grad_loss && target_output && action && coef && grad_target_output, "upgo_backward: null pointer");

@@ -422,6 +422,7 @@ int hpc_rll_vtrace_forward(const float* target_output, const float* behaviour_ou
                            float* pg_coef, float* gv_buf, int64_t T, int64_t B, int64_t N, double gamma,
                            double lambda, double rho_clip_ratio, double c_clip_ratio, double rho_pg_clip_ratio,
                            int64_t global_B, void* workspace, size_t workspace_bytes, void* stream_) {
+    HPC_NVTX("vtrace_forward");
     using namespace hpcrll;
     cudaStream_t stream = as_stream(stream_);
     HPC_REQUIRE(T > 0 && B > 0 && N > 0, "vtrace_forward: sizes must be positive (T=%lld B=%lld N=%lld)",
@@ -547,6 +548,7 @@ int hpc_rll_vtrace_backward(const float* grad_policy_loss, const float* grad_val
                             const float* grad_entropy_loss, const float* target_output, const int64_t* action,
                             const float* weight, const float* pg_coef, const float* gv_buf, float* grad_target_output,
                             float* grad_value, int64_t T, int64_t B, int64_t N, int64_t global_B, void* stream_) {
+    HPC_NVTX("vtrace_backward");
     using namespace hpcrll;
     cudaStream_t stream = as_stream(stream_);
     HPC_REQUIRE(T > 0 && B > 0 && N > 0, "vtrace_backward: sizes must be positive");
