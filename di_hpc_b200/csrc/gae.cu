@@ -661,7 +661,7 @@ static int launch_bwd_tma_st(const float* grad_adv, int64_t ldg, const float* dt
 //   3: BT=64  TT=32 ST=3      4: BT=128 TT=8  ST=4     5: BT=64 TT=8  ST=6
 //   6: BT=128 TT=32 ST=3      7: BT=256 TT=8  ST=4     8: BT=256 TT=16 ST=3
 //  10: BT=256 TT=4  ST=8     11: BT=256 TT=8  ST=6     13: BT=32 TT=64 ST=6   14: BT=32 TT=16 ST=12
-//  21: single-launch T-split with look-back (automatic for B <= 4096, T >= 32; 20 = its old two-launch name)   99: generic (non-TMA) kernel
+//  21: single-launch T-split with look-back (automatic for B <= 2048, T >= 512; 20 = its old two-launch name)   99: generic (non-TMA) kernel
 //  30..34: TMA-staged OUTPUT as well (ScanPipeOut; results leave as (TT x BT) bulk stores):
 //  30: BT=256 TT=8 ST=4    31: BT=128 TT=16 ST=3    32: BT=256 TT=16 ST=3    33: BT=256 TT=4 ST=6    34: BT=256 TT=4 ST=5
 //  35: BT=64 TT=16 ST=4    36: BT=128 TT=8 ST=5     37: BT=64 TT=8 ST=6       38: BT=128 TT=4 ST=8   (mid-size batches)
