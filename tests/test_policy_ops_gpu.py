@@ -317,3 +317,21 @@ def test_small_batch_tsplit_agrees_with_column_scan(T, B, N, use_w):
     assert a[1][0] == b[1][0] and np.array_equal(a[1][1], b[1][1])
     # UPGO's coefficient is 0/1: composing segments is exact, the T-split must give the column scan's bits
     assert np.array_equal(res[21][0][1][1], res[2][0][1][1])
+
+
+def test_ppo_lazy_info_matches_eager_floats():
+    """PPO.lazy_info: approx_kl / clipfrac as LazyScalars (8-byte D2H copy queued next to an event, host waits only when the
+    value is read) must equal the reference-style Python floats of the default mode."""
+    need_cuda()
+    from hpc_rll.rl_utils.ppo import PPO, LazyScalar
+    inp = ppo_inputs(rng(5), 777, 6, True)
+    args = [dev(inp[k]) for k in ("logits_new", "logits_old", "action", "value_new", "value_old", "adv", "return_", "weight")]
+    eager = PPO(777, 6)
+    lazy = PPO(777, 6)
+    lazy.lazy_info = True
+    _, info_e = eager(*args, 0.2, True, None)
+    loss_l, info_l = lazy(*args, 0.2, True, None)
+    assert isinstance(info_e.approx_kl, float) and isinstance(info_l.approx_kl, LazyScalar)
+    assert float(info_l.approx_kl) == info_e.approx_kl and float(info_l.clipfrac) == info_e.clipfrac
+    assert info_l.clipfrac.ready() and (info_l.clipfrac + 1.0) == info_e.clipfrac + 1.0 and info_l.approx_kl < 10.0
+    assert "%.4f" % info_l.approx_kl == "%.4f" % info_e.approx_kl
