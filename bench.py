@@ -529,7 +529,7 @@ def run_ours(args):
     # ---- the path's only collective: a loss op on the local shard, scalar all-reduced ----------------------
     loss_ar = None
     if dist is not None and not args.no_extras:
-        from di_hpc_b200.sharding import all_reduce_losses, set_global_batch
+        from di_hpc_b200.sharding import P2PScalarAllReduce, all_reduce_losses, set_global_batch
         from hpc_rll.rl_utils.td import TDLambda
         vl = torch.randn(T + 1, B, device=dev, generator=gen).requires_grad_(True)
         rl = torch.randn(T, B, device=dev, generator=gen)
@@ -543,8 +543,18 @@ def run_ours(args):
             (loss, ) = all_reduce_losses([tdl(vl, rl)])
             torch.autograd.grad(loss, [vl], grad_outputs=one)
 
-        res = {}
-        for name, fn in (("local_only_ms", td_local), ("with_allreduce_ms", td_global)):
+        p2p = P2PScalarAllReduce()
+
+        def td_global_p2p():
+            (loss, ) = all_reduce_losses([tdl(vl, rl)], comm=p2p)
+            torch.autograd.grad(loss, [vl], grad_outputs=one)
+
+        # same numbers from both collectives (rank-ordered fp32 sum vs NCCL's)
+        la = all_reduce_losses([tdl(vl, rl)])[0].item()
+        lb = all_reduce_losses([tdl(vl, rl)], comm=p2p)[0].item()
+        res = {"loss_nccl": la, "loss_p2p": lb}
+        for name, fn in (("local_only_ms", td_local), ("with_allreduce_ms", td_global),
+                         ("with_p2p_allreduce_ms", td_global_p2p)):
             for _ in range(3):
                 fn()
             barrier()
@@ -556,8 +566,11 @@ def run_ours(args):
             barrier()
             res[name] = max_over_ranks(a.elapsed_time(b)) / 20
         res["what"] = ("TD(lambda) fwd+bwd T=%d B_local=%d, loss normalised by the global count; with_allreduce adds one "
-                       "NCCL all_reduce(SUM) of the scalar loss per step (di_hpc_b200.sharding.all_reduce_losses)" % (T, B))
+                       "NCCL all_reduce(SUM) of the scalar loss per step, with_p2p_allreduce the NVLink peer-memory kernel "
+                       "(csrc/p2p.cu) instead (di_hpc_b200.sharding.all_reduce_losses)" % (T, B))
         res["allreduce_cost_ms"] = res["with_allreduce_ms"] - res["local_only_ms"]
+        res["p2p_allreduce_cost_ms"] = res["with_p2p_allreduce_ms"] - res["local_only_ms"]
+        p2p.close()
         loss_ar = res
         del vl, rl
         torch.cuda.empty_cache()

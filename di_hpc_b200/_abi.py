@@ -58,6 +58,12 @@ SIGNATURES = {
     "hpc_rll_qrdqn_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 3 + [c_vp]),
     "hpc_rll_iqn_nstep_td_forward": (c_int, [c_vp] * 12 + [c_i64] * 5 + [c_dbl, c_dbl, c_i64, c_vp, c_sz, c_vp]),
     "hpc_rll_iqn_nstep_td_backward": (c_int, [c_vp] * 4 + [c_i64] * 3 + [c_vp]),
+    "hpc_rll_p2p_buffer_bytes": (c_sz, []),
+    "hpc_rll_p2p_alloc": (c_int, [c_vp, c_vp]),
+    "hpc_rll_p2p_open": (c_int, [c_vp, c_vp]),
+    "hpc_rll_p2p_close": (c_int, [c_vp]),
+    "hpc_rll_p2p_free": (c_int, [c_vp]),
+    "hpc_rll_allreduce_scalars_p2p": (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_vp]),
     "hpc_rll_pad_batch": (c_int, [c_vp] * 5 + [c_i64, c_int, c_vp]),
     "hpc_rll_unpad_batch": (c_int, [c_vp] * 4 + [c_i64, c_vp]),
     "hpc_rll_oracle_split_group": (c_int, [c_vp, c_i64, c_int, c_int, c_vp]),

@@ -265,6 +265,22 @@ int hpc_rll_iqn_nstep_td_forward(const float* q, const float* next_n_q, const in
 int hpc_rll_iqn_nstep_td_backward(const float* grad_loss, const float* grad_buf, const int64_t* action,
                                   float* grad_q, int64_t tau, int64_t B, int64_t N, void* stream);
 
+/* ---- the path's only collective: all-reduce(SUM) of <= 16 loss scalars over NVLink peer memory -------------------
+ * Batch-sharded loss ops (kernels normalise by `global_B`) end in a sum of a few scalars over the ranks.  Instead of an NCCL
+ * call, every rank owns a small device buffer its peers have mapped through CUDA IPC; one tiny kernel per rank stores
+ * its epoch-tagged scalars into every peer's buffer, waits for all ranks' words in its own buffer and adds them in RANK
+ * ORDER (bit-identical on every rank, run to run).  Set-up (once per process group):
+ *   hpc_rll_p2p_alloc  -> local buffer + 64-byte IPC handle; exchange the handles (e.g. torch.distributed.all_gather);
+ *   hpc_rll_p2p_open   -> a mapping of each peer's buffer;  bufs[r] = peer mapping, bufs[rank] = the local buffer.
+ * hpc_rll_allreduce_scalars_p2p reduces vals[0..n) (device, fp32) in place on `stream`; every rank must issue the same
+ * sequence of calls.  Capturable in CUDA graphs (the epoch lives on the device).  di_hpc_b200/sharding.py wraps it. */
+size_t hpc_rll_p2p_buffer_bytes(void);
+int hpc_rll_p2p_alloc(void** local_buf, void* ipc_handle_64);
+int hpc_rll_p2p_open(const void* ipc_handle_64, void** peer_buf);
+int hpc_rll_p2p_close(void* peer_buf);
+int hpc_rll_p2p_free(void* local_buf);
+int hpc_rll_allreduce_scalars_p2p(float* vals, int n, void* const* bufs, int rank, int world, void* stream);
+
 /* ---- ragged-tensor padding (the data format on the input side of the path) -----------------------
  * replaces Pad{1,2,3}DForward / GroupPad{1,2,3}DForward / Unpad{1,2,3}DForward and the two group splitters
  * (/root/reference/src/rl_utils/padding.cu:8-589, kernels include/hpc/rll/cuda/rl_utils/padding_kernel.h:100-233);
