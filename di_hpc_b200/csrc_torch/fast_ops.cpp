@@ -411,9 +411,33 @@ struct IqnFn : public Function<IqnFn> {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ P2P all-reduce
+// all-reduce(SUM) of <= 16 loss scalars over NVLink peer memory (csrc/p2p.cu); gradient = identity.  `bufs_addr` is the
+// address of the host array of `world` device pointers held by di_hpc_b200.sharding.P2PScalarAllReduce.
+struct P2PAllReduceFn : public Function<P2PAllReduceFn> {
+    static Tensor forward(AutogradContext*, const Tensor& x, int64_t bufs_addr, int64_t rank, int64_t world) {
+        TORCH_CHECK(x.is_cuda() && x.numel() >= 1 && x.numel() <= 16, "p2p all-reduce takes 1..16 CUDA scalars");
+        c10::cuda::CUDAGuard guard(x.device());
+        Tensor y = x.detach().to(torch::kFloat32).contiguous().clone();
+        ck(hpc_rll_allreduce_scalars_p2p(y.data_ptr<float>(), static_cast<int>(y.numel()),
+                                         reinterpret_cast<void* const*>(bufs_addr), static_cast<int>(rank),
+                                         static_cast<int>(world), cur_stream()),
+           "hpc_rll_allreduce_scalars_p2p");
+        return y;
+    }
+    static variable_list backward(AutogradContext*, variable_list grads) {
+        return {grads[0], Tensor(), Tensor(), Tensor()};
+    }
+};
+
 }  // namespace
 
 void register_fast_ops(pybind11::module& m) {
+    m.def("allreduce_scalars_p2p",
+          [](const Tensor& x, int64_t bufs_addr, int64_t rank, int64_t world) {
+              return P2PAllReduceFn::apply(x, bufs_addr, rank, world);
+          },
+          "all-reduce(SUM) of <= 16 scalars over NVLink peer memory, differentiable (identity gradient)");
     namespace py = pybind11;
     m.def("gae", [](const Tensor& v, const Tensor& r, double g, double l) { return GaeFn::apply(v, r, g, l); },
           "GAE forward with autograd (adjoint) -- C++ twin of GAEFunction");

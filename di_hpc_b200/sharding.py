@@ -13,7 +13,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-from . import _abi
+from . import _abi, _ext
 
 
 def shard_columns(B: int, rank: int, world: int, align: int = 4) -> Tuple[int, int]:
@@ -132,7 +132,11 @@ def all_reduce_losses(losses: Sequence[torch.Tensor], group=None, comm: Optional
     flat = losses[0].reshape(-1) if len(losses) == 1 else torch.cat([l.reshape(-1) for l in losses])
     comm = comm if comm is not None else _default_comm
     if comm is not None and flat.is_cuda and flat.numel() <= 16:
-        red = _AllReduceSumP2P.apply(flat, comm)
+        fast = _ext.fast()
+        if fast is not None and hasattr(fast, "allreduce_scalars_p2p"):  # C++ autograd function: no Python bookkeeping
+            red = fast.allreduce_scalars_p2p(flat, ctypes.addressof(comm._bufs), comm.rank, comm.world)
+        else:
+            red = _AllReduceSumP2P.apply(flat, comm)
     else:
         red = _AllReduceSum.apply(flat, group)
     out, o = [], 0

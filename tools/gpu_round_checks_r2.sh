@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2: everything a round wants from ONE single-GPU gpurun call (about 10 GPU-minutes), results under gpurun_out/:
-#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_r2_final.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_round_checks_r2.sh'
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -q -m gpu 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.txt
