@@ -70,7 +70,7 @@ void count_launch(int n = 1);
 // ----------------------------------------------------------------------------------------------
 bool tma_ok_2d(const void* base, int64_t cols, int64_t ld);
 int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                 int box_cols);
+                 int box_cols, bool swizzle128 = false);  // swizzle128: CU_TENSOR_MAP_SWIZZLE_128B (box_cols <= 32)
 
 // Opt a kernel into > 48 KB dynamic shared memory.  The attribute is per context and holds the LARGEST byte count
 // granted so far per device: kernels whose dynamic size varies at run time (n_atom / tau dependent, nstep.cu) are
@@ -160,6 +160,24 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int col0, i
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
                      reinterpret_cast<uint64_t>(map)),
                  "r"(col0), "r"(row0), "r"(smem_u32(src))
+                 : "memory");
+}
+// 1-D bulk copy smem -> global (bytes % 16 == 0, both 16B aligned); completion by bulk async-groups as above
+__device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst)),
+                 "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+// same with an L2 eviction-priority hint (createpolicy): data the next kernel re-reads should stay resident
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_store_1d_hint(void* dst, const void* src, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(
+                     reinterpret_cast<uint64_t>(dst)),
+                 "r"(smem_u32(src)), "r"(bytes), "l"(policy)
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

@@ -242,10 +242,30 @@ def test_iqn_vs_golden(name):
         close_grad(gq, c.grad("q", prec), "grad_q")
 
 
-@pytest.mark.parametrize("cfg", [0, 1])
+@pytest.mark.parametrize("n_atom", [2, 3, 4, 5, 31, 32, 33, 61, 62, 63, 64, 65, 127, 128, 129, 200])
+def test_dist_atom_counts(n_atom):
+    """every row length around the 32-atom segment / 4-float group boundaries of the TMA-gather kernel (rows start at
+    any of the four 16-byte phases: N * n_atom and the actions vary), a batch with a partial warp, and the hand-over to
+    the warp-per-sample kernel above 128 atoms"""
+    need_cuda()
+    g = rng(4000 + n_atom)
+    T, B, N = 3, 77, 3
+    inp = base_inputs(g, T, B, N, True)
+    inp["reward"] = (inp["reward"] * 3).astype(np.float32)
+    inp["dist"] = softmax(g.standard_normal((B, N, n_atom)))
+    inp["next_n_dist"] = softmax(g.standard_normal((B, N, n_atom)))
+    loss, td, gd = run_dist(inp, 0.97, -4.0, 6.0, 1.0)
+    o = orc.dist_nstep_td(inp["dist"], inp["next_n_dist"], inp["action"], inp["next_n_action"], inp["reward"],
+                          inp["done"], inp["weight"], 0.97, -4.0, 6.0, 1.0)
+    close(loss, o["loss"], "loss")
+    close(td, o["td_error_per_sample"], "td")
+    close_grad(gd, o["grad_dist"], "grad_dist")
+
+
+@pytest.mark.parametrize("cfg", [1, 2])
 def test_dist_kernel_variants(cfg):
-    """warp-per-sample (0) and lane-per-sample (1) C51 kernels against the oracle, incl. done=1 rows whose whole
-    mass lands on one atom and a batch that is not a multiple of the 128-sample tile."""
+    """lane-per-sample (1) and warp-per-sample (2) C51 kernels against the oracle, incl. done=1 rows whose whole
+    mass lands on one atom and a batch that is not a multiple of the sample tile."""
     need_cuda()
     from di_hpc_b200 import _abi
     g = rng(cfg + 900)
