@@ -120,7 +120,7 @@ def main():
         q = r(B, N).requires_grad_(True)
         act, nact = a[0], torch.randint(0, N, (B, ), device=D)
         done = (torch.rand(B, device=D) < 0.3).float()
-        for dcfg in (0, 1):
+        for dcfg in (1, 2):  # lane-per-sample (TMA-gathered rows) and warp-per-sample C51 kernels
             _abi.set_config(6, dcfg)
             dd = torch.softmax(r(B, N, 21), -1).requires_grad_(True)
             torch.autograd.grad(DistNStepTD(T, B, N, 21)(dd, torch.softmax(r(B, N, 21), -1), act, nact, rew.detach(), done, None, 0.9, -3., 3.)[0], [dd], grad_outputs=ONE)
@@ -140,6 +140,12 @@ def main():
             torch.autograd.grad(
                 IQNNStepTDError(tau, tau + 1, T, B, N)(qi, r(tau + 1, B, N), act, nact, rew.detach(), done,
                                                        torch.rand(tau, B, device=D), 0.95, 0.9)[0], [qi], grad_outputs=ONE)
+    # round 2: the backward scatter from shared-memory images (taken from 1 MB of output on), one case per mapping
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from tests.test_scatter_gpu import run as scatter_case
+    for case in (("q", 40003, 8, 1, 1), ("q", 9001, 40, 1, 1), ("iqn", 5003, 8, 1, 13), ("dist", 9001, 4, 7, 1),
+                 ("dist", 3001, 8, 51, 1), ("qrdqn", 2003, 8, 64, 1), ("qrdqn", 1203, 5, 130, 1)):
+        scatter_case(*case)
     data = [r(int(torch.randint(3, 20, (1, ))), int(torch.randint(2, 17, (1, )))) for _ in range(40)]
     x, m, s = Padding2D(data)
     UnPadding2D(x, s)
