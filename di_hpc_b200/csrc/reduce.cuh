@@ -63,7 +63,15 @@ __global__ void __launch_bounds__(256) finalize_sums(const double* __restrict__ 
 #pragma unroll
     for (int k = 0; k < NT; ++k) {
         double a = 0.0;
-        for (int i = threadIdx.x; i < n; i += 256) a += partials[static_cast<size_t>(k) * n + i];
+        const double* p = partials + static_cast<size_t>(k) * n;
+        for (int i0 = threadIdx.x; i0 < n; i0 += 256 * 8) {  // 8 loads in flight, adds in the original order
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = __ldcg(p + min(i0 + u * 256, n - 1));  // clamped index: no predicate
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 + u * 256 < n) a += x[u];
+        }
         v[k] = a;
     }
     block_sum<NT>(v, scratch);
