@@ -262,6 +262,23 @@ def test_dist_atom_counts(n_atom):
     close_grad(gd, o["grad_dist"], "grad_dist")
 
 
+def test_dist_many_samples_short_rows():
+    """short rows make the lane kernel's CTAs small enough for > 16 per SM: the grid (and with it the number of loss
+    partials in the workspace) must stay within what the workspace holds"""
+    need_cuda()
+    g = rng(4242)
+    T, B, N, n_atom = 2, 300001, 2, 5
+    inp = base_inputs(g, T, B, N, False)
+    inp["dist"] = softmax(g.standard_normal((B, N, n_atom)))
+    inp["next_n_dist"] = softmax(g.standard_normal((B, N, n_atom)))
+    loss, td, gd = run_dist(inp, 0.9, -1.0, 2.0, 1.0)
+    o = orc.dist_nstep_td(inp["dist"], inp["next_n_dist"], inp["action"], inp["next_n_action"], inp["reward"],
+                          inp["done"], inp["weight"], 0.9, -1.0, 2.0, 1.0)
+    close(loss, o["loss"], "loss")
+    close(td, o["td_error_per_sample"], "td")
+    close_grad(gd, o["grad_dist"], "grad_dist")
+
+
 @pytest.mark.parametrize("cfg", [1, 2])
 def test_dist_kernel_variants(cfg):
     """lane-per-sample (1) and warp-per-sample (2) C51 kernels against the oracle, incl. done=1 rows whose whole
