@@ -26,9 +26,14 @@ struct PpoParams {
 // (adv - mean) / (std + 1e-8) with the statistics of hpc_rll_adv_stats; identity when there are none
 struct AdvNorm {
     float mean, denom;
+    bool has;
     __device__ __forceinline__ explicit AdvNorm(const PpoParams& P)
-        : mean(P.adv_stats ? __ldg(P.adv_stats) : 0.f), denom(P.adv_stats ? __ldg(P.adv_stats + 1) : 1.f) {}
-    __device__ __forceinline__ float operator()(float a) const { return __fdiv_rn(__fsub_rn(a, mean), denom); }
+        : mean(P.adv_stats ? __ldg(P.adv_stats) : 0.f), denom(P.adv_stats ? __ldg(P.adv_stats + 1) : 1.f),
+          has(P.adv_stats != nullptr) {}
+    // (no statistics: (a - 0) / 1 == a exactly, so the IEEE division is skipped -- a block-uniform branch)
+    __device__ __forceinline__ float operator()(float a) const {
+        return has ? __fdiv_rn(__fsub_rn(a, mean), denom) : a;
+    }
 };
 
 // scalar part for one sample; returns the five loss terms' contributions and the two coefficients
@@ -82,7 +87,10 @@ constexpr int ppo_min_blocks(int kmax, int width) {
     return ne >= 32 ? 1 : ((ne >= 20 || (ne == 8 && kmax >= 4)) ? 2 : 3);
 }
 
-template <int KMAX, int WIDTH>
+// G1: one lane per row (G == 1, N == KMAX * WIDTH exactly) known at compile time -- the group loops, the `e0 < N`
+// predicates and the element-index arithmetic of the row helpers fold away (the kernel is bound by instruction issue
+// at small N: profiles/r02_ppo_small_n.md).
+template <int KMAX, int WIDTH, bool G1 = false>
 __global__ void __launch_bounds__(256, ppo_min_blocks(KMAX, WIDTH)) ppo_rows_fwd(const float* __restrict__ logits_new,
                                                      const float* __restrict__ logits_old,
                                                      const int64_t* __restrict__ action,
@@ -91,11 +99,12 @@ __global__ void __launch_bounds__(256, ppo_min_blocks(KMAX, WIDTH)) ppo_rows_fwd
                                                      const float* __restrict__ adv, const float* __restrict__ ret,
                                                      const float* __restrict__ weight, float* __restrict__ pol_coef,
                                                      float* __restrict__ val_coef, double* __restrict__ partials,
-                                                     const PpoParams P, int64_t R, int N, int G, int log2G) {
+                                                     const PpoParams P, int64_t R, int N_, int G_, int log2G_) {
     using Row = RowRegs<KMAX, WIDTH>;
     __shared__ double red[5 * 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lig = lane & (G - 1), gw = lane >> log2G;
+    const int N = G1 ? KMAX * WIDTH : N_, G = G1 ? 1 : G_, log2G = G1 ? 0 : log2G_;
+    const int lig = G1 ? 0 : (lane & (G - 1)), gw = lane >> log2G;
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
     double acc[5] = {0, 0, 0, 0, 0};
@@ -121,19 +130,24 @@ __global__ void __launch_bounds__(256, ppo_min_blocks(KMAX, WIDTH)) ppo_rows_fwd
         return sc;
     };
     Scal cur, nxt;
-    {
-        const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
-        rn.load(logits_new + row0 * N, N, G, lig, row0 < R);
-        ro.load(logits_old + row0 * N, N, G, lig, row0 < R);
-        cur = load_scal(row0);
-    }
-    for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
-        const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
+    // row index and row pointers advance by increments (no 64-bit multiply per row)
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * rows_per_block;
+    int64_t base = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+    int64_t row = base + warp * rows_per_warp + gw;
+    const float* pn = logits_new + row * N;
+    const float* po = logits_old + row * N;
+    const int64_t pstep = stride * N;
+    rn.load(pn, N, G, lig, row < R);
+    ro.load(po, N, G, lig, row < R);
+    cur = load_scal(row);
+    for (; base < R; base += stride, row += stride) {  // block-uniform trip count
         const bool active = row < R;
-        const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
+        const int64_t nrow = row + stride;
+        pn += pstep;
+        po += pstep;
         if (PF) {
-            nn.load(logits_new + nrow * N, N, G, lig, nrow < R);
-            no.load(logits_old + nrow * N, N, G, lig, nrow < R);
+            nn.load(pn, N, G, lig, nrow < R);
+            no.load(po, N, G, lig, nrow < R);
         }
         nxt = load_scal(nrow);
         const int a = cur.a;
@@ -155,8 +169,8 @@ __global__ void __launch_bounds__(256, ppo_min_blocks(KMAX, WIDTH)) ppo_rows_fwd
             rn = nn;
             ro = no;
         } else {
-            rn.load(logits_new + nrow * N, N, G, lig, nrow < R);
-            ro.load(logits_old + nrow * N, N, G, lig, nrow < R);
+            rn.load(pn, N, G, lig, nrow < R);
+            ro.load(po, N, G, lig, nrow < R);
         }
         cur = nxt;
     }
@@ -297,9 +311,17 @@ static int ppo_forward_impl(const float* logits_new, const float* logits_old, co
     const bool staged = use_staged_rows(N, ge.width);
     const unsigned grid = rows_grid(B, staged ? kStageRows : (ge.kmax == 0 ? 8 : (32 / ge.G) * 8));
     const int n = static_cast<int>(N);
-#define HPC_PPO_ROWS(K, V)                                                                                       \
-    ppo_rows_fwd<K, V><<<grid, 256, 0, stream>>>(logits_new, logits_old, action, value_new, value_old, adv, return_, \
-                                                 weight, pol_coef, val_coef, partials, P, B, n, ge.G, log2G)
+#define HPC_PPO_ROWS(K, V)                                                                                          \
+    do {                                                                                                            \
+        if (ge.G == 1)                                                                                              \
+            ppo_rows_fwd<K, V, true><<<grid, 256, 0, stream>>>(logits_new, logits_old, action, value_new, value_old, \
+                                                               adv, return_, weight, pol_coef, val_coef, partials, P, \
+                                                               B, n, 1, 0);                                           \
+        else                                                                                                        \
+            ppo_rows_fwd<K, V, false><<<grid, 256, 0, stream>>>(logits_new, logits_old, action, value_new,           \
+                                                                value_old, adv, return_, weight, pol_coef, val_coef, \
+                                                                partials, P, B, n, ge.G, log2G);                     \
+    } while (0)
     if (staged) {
         static SmemOptIn opt;
         if (int rc0 = opt.ensure(ppo_rows_fwd_staged, static_cast<int>(stage_bytes(32, 2)))) return rc0;  // largest pitch (N=32 -> 33)

@@ -8,19 +8,21 @@
 
 namespace hpcrll {
 
-template <int KMAX, int WIDTH, bool ENT, bool CAT>
+// G1: one lane per row known at compile time (G == 1, N == KMAX * WIDTH): see ppo_rows_fwd
+template <int KMAX, int WIDTH, bool ENT, bool CAT, bool G1 = false>
 __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __restrict__ logits,
                                                                  const int64_t* __restrict__ action,
                                                                  const float* __restrict__ c1,
                                                                  const float* __restrict__ w,
                                                                  const float* __restrict__ g1,
                                                                  const float* __restrict__ g2, float inv_n,
-                                                                 float* __restrict__ grad, int64_t R, int N, int G,
-                                                                 int log2G) {
+                                                                 float* __restrict__ grad, int64_t R, int N_, int G_,
+                                                                 int log2G_) {
     using Row = RowRegs<KMAX, WIDTH>;
     constexpr int W = Row::W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lig = lane & (G - 1), gw = lane >> log2G;
+    const int N = G1 ? KMAX * WIDTH : N_, G = G1 ? 1 : G_, log2G = G1 ? 0 : log2G_;
+    const int lig = G1 ? 0 : (lane & (G - 1)), gw = lane >> log2G;
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
     const float s1 = __ldg(g1);
@@ -28,15 +30,19 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
     // software pipeline (small rows only): the next row block's loads fly while this one is reduced
     constexpr bool PF = Row::NE <= 8;
     Row rr, nx;
-    {
-        const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
-        rr.load(logits + row0 * N, N, G, lig, row0 < R);
-    }
-    for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
-        const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
+    // row index and row pointers advance by increments (no 64-bit multiply per row)
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * rows_per_block;
+    int64_t base = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+    int64_t row = base + warp * rows_per_warp + gw;
+    const float* pl = logits + row * N;
+    float* pg = grad + row * N;
+    const int64_t pstep = stride * N;
+    rr.load(pl, N, G, lig, row < R);
+    for (; base < R; base += stride, row += stride, pg += pstep) {  // block-uniform trip count
         const bool active = row < R;
-        const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
-        if (PF) nx.load(logits + nrow * N, N, G, lig, nrow < R);
+        const int64_t nrow = row + stride;
+        pl += pstep;
+        if (PF) nx.load(pl, N, G, lig, nrow < R);
         const int a = active ? static_cast<int>(action[row]) : -1;
         const float c = active ? s1 * c1[row] : 0.f;
         const float e2 = ENT ? s2 * ((w && active) ? w[row] : 1.f) : 0.f;
@@ -60,16 +66,16 @@ __global__ void __launch_bounds__(256) softmax_grad_rows_kernel(const float* __r
             const int e0 = rr.index(j, 0, G, lig);
             if (active && e0 < N) {
                 if (W == 4)
-                    st_stream4(reinterpret_cast<float4*>(grad + row * N + e0),
+                    st_stream4(reinterpret_cast<float4*>(pg + e0),
                                make_float4(o[0], o[W > 1 ? 1 : 0], o[W > 2 ? 2 : 0], o[W > 3 ? 3 : 0]));
                 else if (W == 2)
-                    st_stream2(reinterpret_cast<float2*>(grad + row * N + e0), make_float2(o[0], o[W > 1 ? 1 : 0]));
+                    st_stream2(reinterpret_cast<float2*>(pg + e0), make_float2(o[0], o[W > 1 ? 1 : 0]));
                 else
-                    st_stream(grad + row * N + e0, o[0]);
+                    st_stream(pg + e0, o[0]);
             }
         }
         if (PF) rr = nx;
-        else rr.load(logits + nrow * N, N, G, lig, nrow < R);
+        else rr.load(pl, N, G, lig, nrow < R);
     }
 }
 
@@ -172,9 +178,16 @@ static int launch_grad_t(const float* logits, const int64_t* action, const float
     while ((1 << log2G) < ge.G) ++log2G;
     const int rows_per_block = (32 / ge.G) * 8;
     const unsigned grid = rows_grid(R, ge.kmax == 0 ? 8 : rows_per_block);
-#define HPC_GRAD_LAUNCH(K, V)                                                                                    \
-    softmax_grad_rows_kernel<K, V, ENT, CAT><<<grid, 256, 0, stream>>>(logits, action, c1, w, g1, g2, inv_n, grad, \
-                                                                       R, N, ge.G, log2G)
+#define HPC_GRAD_LAUNCH(K, V)                                                                                        \
+    do {                                                                                                             \
+        if (ge.G == 1)                                                                                               \
+            softmax_grad_rows_kernel<K, V, ENT, CAT, true><<<grid, 256, 0, stream>>>(logits, action, c1, w, g1, g2,  \
+                                                                                     inv_n, grad, R, N, 1, 0);       \
+        else                                                                                                         \
+            softmax_grad_rows_kernel<K, V, ENT, CAT, false><<<grid, 256, 0, stream>>>(logits, action, c1, w, g1, g2, \
+                                                                                      inv_n, grad, R, N, ge.G,       \
+                                                                                      log2G);                        \
+    } while (0)
     if (ge.kmax == 0)
         softmax_grad_rows_loop_kernel<ENT, CAT><<<grid, 256, 0, stream>>>(logits, action, c1, w, g1, g2, inv_n, grad,
                                                                          R, N);

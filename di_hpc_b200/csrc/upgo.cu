@@ -18,30 +18,35 @@
 
 namespace hpcrll {
 
-template <int KMAX, int WIDTH>
+// G1: one lane per row known at compile time (G == 1, N == KMAX * WIDTH): see ppo_rows_fwd
+template <int KMAX, int WIDTH, bool G1 = false>
 __global__ void __launch_bounds__(256) upgo_rows_fwd(const float* __restrict__ logits,
                                                       const int64_t* __restrict__ action,
-                                                      float* __restrict__ metric, int64_t R, int N, int G,
-                                                      int log2G) {
+                                                      float* __restrict__ metric, int64_t R, int N_, int G_,
+                                                      int log2G_) {
     using Row = RowRegs<KMAX, WIDTH>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lig = lane & (G - 1), gw = lane >> log2G;
+    const int N = G1 ? KMAX * WIDTH : N_, G = G1 ? 1 : G_, log2G = G1 ? 0 : log2G_;
+    const int lig = G1 ? 0 : (lane & (G - 1)), gw = lane >> log2G;
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
     constexpr bool PF = Row::NE <= 8;  // software pipeline (see softmax_rows.cu)
     Row rr, nx;
     int a, na = -1;
-    {
-        const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
-        rr.load(logits + row0 * N, N, G, lig, row0 < R);
-        a = row0 < R ? static_cast<int>(action[row0]) : -1;
-    }
-    for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
-        const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
+    // row index and row pointer advance by increments (no 64-bit multiply per row)
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * rows_per_block;
+    int64_t base = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+    int64_t row = base + warp * rows_per_warp + gw;
+    const float* pl = logits + row * N;
+    const int64_t pstep = stride * N;
+    rr.load(pl, N, G, lig, row < R);
+    a = row < R ? static_cast<int>(action[row]) : -1;
+    for (; base < R; base += stride, row += stride) {  // block-uniform trip count
         const bool active = row < R;
-        const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
+        const int64_t nrow = row + stride;
+        pl += pstep;
         if (PF) {
-            nx.load(logits + nrow * N, N, G, lig, nrow < R);
+            nx.load(pl, N, G, lig, nrow < R);
             na = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
         const float m = rr.row_max(G);
@@ -53,7 +58,7 @@ __global__ void __launch_bounds__(256) upgo_rows_fwd(const float* __restrict__ l
             rr = nx;
             a = na;
         } else {
-            rr.load(logits + nrow * N, N, G, lig, nrow < R);
+            rr.load(pl, N, G, lig, nrow < R);
             a = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
     }
@@ -300,7 +305,14 @@ int hpc_rll_upgo_forward(const float* target_output, const float* rhos, const in
     const bool staged = use_staged_rows(N, ge.width);
     const unsigned grid1 = rows_grid(R, staged ? kStageRows : (ge.kmax == 0 ? 8 : (32 / ge.G) * 8));
     const int n = static_cast<int>(N);
-#define HPC_UP_ROWS(K, V) upgo_rows_fwd<K, V><<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n, ge.G, log2G)
+#define HPC_UP_ROWS(K, V)                                                                                       \
+    do {                                                                                                        \
+        if (ge.G == 1)                                                                                          \
+            upgo_rows_fwd<K, V, true><<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n, 1, 0);    \
+        else                                                                                                    \
+            upgo_rows_fwd<K, V, false><<<grid1, 256, 0, stream>>>(target_output, action, metric, R, n, ge.G,    \
+                                                                  log2G);                                       \
+    } while (0)
     if (staged)
         upgo_rows_fwd_staged<<<grid1, kStageRows, stage_bytes(n, 1), stream>>>(target_output, action, metric, R, n,
                                                                                stage_pitch(n),

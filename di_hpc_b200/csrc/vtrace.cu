@@ -26,17 +26,19 @@ namespace hpcrll {
 // ------------------------------------------------------------------------------------------------
 // forward stage 1: rows
 // ------------------------------------------------------------------------------------------------
-template <int KMAX, int WIDTH>
+// G1: one lane per row known at compile time (G == 1, N == KMAX * WIDTH): see ppo_rows_fwd
+template <int KMAX, int WIDTH, bool G1 = false>
 __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__ target,
                                                         const float* __restrict__ behaviour,
                                                         const int64_t* __restrict__ action,
                                                         const float* __restrict__ weight, float* __restrict__ is_out,
                                                         float* __restrict__ logp_out, double* __restrict__ partials,
-                                                        int64_t R, int N, int G, int log2G) {
+                                                        int64_t R, int N_, int G_, int log2G_) {
     using Row = RowRegs<KMAX, WIDTH>;
     __shared__ double red[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lig = lane & (G - 1), gw = lane >> log2G;
+    const int N = G1 ? KMAX * WIDTH : N_, G = G1 ? 1 : G_, log2G = G1 ? 0 : log2G_;
+    const int lig = G1 ? 0 : (lane & (G - 1)), gw = lane >> log2G;
     const int rows_per_warp = 32 >> log2G;
     const int rows_per_block = rows_per_warp * 8;
     double ent_acc = 0.0;
@@ -44,19 +46,24 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__
     constexpr bool PF = Row::NE <= 8;
     Row rt, rbh, nt, nb;
     int a, na = -1;
-    {
-        const int64_t row0 = static_cast<int64_t>(blockIdx.x) * rows_per_block + warp * rows_per_warp + gw;
-        rt.load(target + row0 * N, N, G, lig, row0 < R);
-        rbh.load(behaviour + row0 * N, N, G, lig, row0 < R);
-        a = row0 < R ? static_cast<int>(action[row0]) : -1;
-    }
-    for (int64_t rb = blockIdx.x; rb * rows_per_block < R; rb += gridDim.x) {
-        const int64_t row = rb * rows_per_block + warp * rows_per_warp + gw;
+    // row index and row pointers advance by increments (no 64-bit multiply per row)
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * rows_per_block;
+    int64_t base = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+    int64_t row = base + warp * rows_per_warp + gw;
+    const float* pt = target + row * N;
+    const float* pb = behaviour + row * N;
+    const int64_t pstep = stride * N;
+    rt.load(pt, N, G, lig, row < R);
+    rbh.load(pb, N, G, lig, row < R);
+    a = row < R ? static_cast<int>(action[row]) : -1;
+    for (; base < R; base += stride, row += stride) {  // block-uniform trip count
         const bool active = row < R;
-        const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * rows_per_block;
+        const int64_t nrow = row + stride;
+        pt += pstep;
+        pb += pstep;
         if (PF) {
-            nt.load(target + nrow * N, N, G, lig, nrow < R);
-            nb.load(behaviour + nrow * N, N, G, lig, nrow < R);
+            nt.load(pt, N, G, lig, nrow < R);
+            nb.load(pb, N, G, lig, nrow < R);
             na = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
         const float mt = rt.row_max(G), mb = rbh.row_max(G);
@@ -78,8 +85,8 @@ __global__ void __launch_bounds__(256) vtrace_rows_fwd(const float* __restrict__
             rbh = nb;
             a = na;
         } else {
-            rt.load(target + nrow * N, N, G, lig, nrow < R);
-            rbh.load(behaviour + nrow * N, N, G, lig, nrow < R);
+            rt.load(pt, N, G, lig, nrow < R);
+            rbh.load(pb, N, G, lig, nrow < R);
             a = nrow < R ? static_cast<int>(action[nrow]) : -1;
         }
     }
@@ -449,9 +456,15 @@ int hpc_rll_vtrace_forward(const float* target_output, const float* behaviour_ou
     const bool staged = use_staged_rows(N, ge.width);
     const unsigned grid1 = rows_grid(R, staged ? kStageRows : (ge.kmax == 0 ? 8 : rows_per_block));
     const int n = static_cast<int>(N);
-#define HPC_VT_ROWS(K, V)                                                                                       \
-    vtrace_rows_fwd<K, V><<<grid1, 256, 0, stream>>>(target_output, behaviour_output, action, weight, is_buf,   \
-                                                     logp_buf, partials, R, n, ge.G, log2G)
+#define HPC_VT_ROWS(K, V)                                                                                             \
+    do {                                                                                                              \
+        if (ge.G == 1)                                                                                                \
+            vtrace_rows_fwd<K, V, true><<<grid1, 256, 0, stream>>>(target_output, behaviour_output, action, weight,   \
+                                                                   is_buf, logp_buf, partials, R, n, 1, 0);           \
+        else                                                                                                          \
+            vtrace_rows_fwd<K, V, false><<<grid1, 256, 0, stream>>>(target_output, behaviour_output, action, weight,  \
+                                                                    is_buf, logp_buf, partials, R, n, ge.G, log2G);   \
+    } while (0)
     if (staged) {
         static SmemOptIn opt;
         if (int rc0 = opt.ensure(vtrace_rows_fwd_staged, static_cast<int>(stage_bytes(32, 2)))) return rc0;  // largest pitch (N=32 -> 33)
